@@ -1,0 +1,258 @@
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (through
+oracle/ref_shim.py) in the build container.  The reference ships no golden vectors
+(SURVEY.md section 4), so these files are the pins for oracle/ and for the CUDA path.
+
+Run:  python oracle/gen_golden.py        (needs /root/reference; CPU only, ~1 min)
+
+Every fixture stores the library versions it was produced with.
+"""
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+import scipy
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+import eeg_oracle as O  # noqa: E402
+import golden_inputs as GI  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+VERS = dict(scipy=scipy.__version__, numpy=np.__version__, torch=torch.__version__)
+
+
+def save(name, **arrs):
+    arrs["_versions"] = np.array(repr(VERS))
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **arrs)
+    print(f"wrote {name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def ref_preproc(ns, raw, label, band, upto="segment"):
+    """Run the reference's DataLoadEEG stages on raw [trials][ch][time] (values upcast
+    to f64 exactly, presented in the .mat's (time, ch, trials) F-order view)."""
+    D = ns.Dataload_eeg.DataLoadEEG(subject=1, band=band, fs_orig=500, fs_target=100)
+    cnt = np.transpose(raw.astype(np.float64), (2, 1, 0))        # (time, ch, trials), F-contiguous
+    D.label = label
+    D.seg = np.transpose(cnt, [1, 0, 2])                          # Dataload_eeg.py:82
+    D.downsampling()
+    dec = D.seg.copy()
+    D.bandpass_filter()
+    if upto == "filter":
+        return dec, D.seg_f
+    D.segment_and_select_classes()
+    return dec, D.seg_f_div, D.label_div
+
+
+def gen_preproc(ns):
+    # (1) small free-shape case: downsampling + bandpass only (segment hard-codes 30/500/4/200)
+    rng = np.random.default_rng(7)
+    raw = rng.standard_normal((6, 4, 1000)).astype(np.float32)
+    raw += (3.0 * np.sin(2 * np.pi * 0.2 * np.arange(6000) / 500.0)).reshape(6, 1, 1000).astype(np.float32)
+    out = {"raw": raw}
+    for tag, band in (("b0545", [0.5, 45]), ("b0530", [5, 30])):
+        dec, filt = ref_preproc(ns, raw, None, band, upto="filter")
+        out["dec"] = dec                      # (4, 200, 6)  (ch, t, trials)
+        out["filt_" + tag] = filt
+    save("preproc_small.npz", **out)
+
+    # (2) dataset-shaped subject 1: digest of the reference's prepare_data output
+    raw, label = O.synth_subject(1)
+    dec, x, y = ref_preproc(ns, raw, label, [0.5, 45])
+    save("preproc_subject1_digest.npz",
+         label=label.astype(np.uint8), y=y.astype(np.int64),
+         x_sub=x[::25, ::7, ::20].copy(),              # strided sample of (400, 30, 500)
+         x_epoch_sum=x.sum(axis=(1, 2)), x_chan_rms=np.sqrt((x ** 2).mean(axis=(0, 2))),
+         raw_checksum=np.array([float(raw.astype(np.float64).sum()), float(np.abs(raw).astype(np.float64).sum())]),
+         dec_sub=dec[::7, ::50, ::25].copy())
+    # (3) index-coded run of segment_and_select_classes: proves epoch e=4k+q <- trial k, [500q,500q+500)
+    D = ns.Dataload_eeg.DataLoadEEG()
+    c, t, k = np.meshgrid(np.arange(30), np.arange(2000), np.arange(200), indexing="ij")
+    D.seg_f = (c * 2000 * 200 + t * 200 + k).astype(np.float64)
+    D.label = label
+    D.segment_and_select_classes()
+    code = D.seg_f_div.astype(np.int64)                 # (400, 30, 500) of source codes
+    src_c, rem = code // (2000 * 200), code % (2000 * 200)
+    src_t, src_k = rem // 200, rem % 200
+    assert (src_c == np.arange(30)[None, :, None]).all()
+    assert (src_k == src_k[:, :1, :1]).all() and ((src_t - np.arange(500)[None, None, :]) == (src_t[:, :1, :1])).all()
+    save("segment_plan.npz", label=label.astype(np.uint8), y=D.label_div.astype(np.int64),
+         src_trial=src_k[:, 0, 0].copy(), src_t0=src_t[:, 0, 0].copy())
+
+    # (4) split: reference get_split on index-coded features, shipped labels and remapped labels
+    for tag, yy in (("shipped", y), ("remap", (y - 1) // 2)):
+        xs = np.arange(yy.size, dtype=np.float64).reshape(-1, 1, 1) * np.ones((1, 2, 3))
+        outs = {}
+        for h in (40, 56):
+            sp = ns.EAV_datasplit.EAVDataSplit(xs, yy)
+            trx, try_, tex, tey = sp.get_split(h_idx=h)
+            outs[f"tr_idx_{h}"] = trx[:, 0, 0].astype(np.int64)
+            outs[f"te_idx_{h}"] = tex[:, 0, 0].astype(np.int64)
+            outs[f"tr_y_{h}"] = try_
+            outs[f"te_y_{h}"] = tey
+        save(f"split_{tag}.npz", y=yy, **outs)
+
+
+def grads_of(model, names):
+    sd = dict(model.named_parameters())
+    return {f"grad::{k}": sd[k].grad.detach().numpy().copy() for k in names}
+
+
+def gen_eegnet_tor(ns):
+    import eegnet_oracle as EO
+    M = ns.EEGNet_tor
+    for tag, B, scale in (("b8", 8, 1.0), ("b8_renorm", 8, 4.0)):
+        torch.manual_seed(3)
+        model = ref_shim.make_eegnet_tor(ns, 5)
+        if scale != 1.0:
+            with torch.no_grad():
+                model.depthwiseConv.weight.mul_(scale)
+                model.dense.weight.mul_(scale)
+        # non-trivial BN affine + running stats so eval mode is exercised properly
+        g = torch.Generator().manual_seed(11)
+        with torch.no_grad():
+            for bn in (model.firstBN, model.depthwiseBN, model.separableBN):
+                bn.weight.copy_(1 + 0.2 * torch.randn(bn.weight.shape, generator=g))
+                bn.bias.copy_(0.1 * torch.randn(bn.bias.shape, generator=g))
+                bn.running_mean.copy_(0.05 * torch.randn(bn.bias.shape, generator=g))
+                bn.running_var.copy_(1 + 0.3 * torch.rand(bn.bias.shape, generator=g))
+        init = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        x = torch.randn(B, 1, 30, 500, generator=g)
+        y = torch.randint(0, 5, (B,), generator=g)
+        out = dict(init, x=x.numpy(), y=y.numpy())
+        crit = torch.nn.CrossEntropyLoss()
+        for mode in ("train", "eval"):
+            model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in init.items()})
+            model.train(mode == "train")
+            model.zero_grad()
+            torch.manual_seed(100)
+            # record the dropout masks the reference draws (order: mask1, mask2) by replaying the RNG
+            if mode == "train":
+                m1 = torch.empty(B, 64, 1, 125).bernoulli_(0.5)
+                m2 = torch.empty(B, 64, 1, 15).bernoulli_(0.5)
+                out["mask1"], out["mask2"] = m1.numpy().astype(np.uint8), m2.numpy().astype(np.uint8)
+                torch.manual_seed(100)
+            p = model(x)
+            loss = crit(p, y)
+            loss.backward()
+            out[f"{mode}::probs"] = p.detach().numpy()
+            out[f"{mode}::loss"] = np.array(loss.item(), dtype=np.float64)
+            for k, v in grads_of(model, EO.TOR_PARAMS).items():
+                out[f"{mode}::{k}"] = v
+            for k, v in model.state_dict().items():
+                if "running" in k or "num_batches" in k or k in ("depthwiseConv.weight", "dense.weight"):
+                    out[f"{mode}::after::{k}"] = v.detach().numpy().copy()
+        save(f"eegnet_tor_{tag}.npz", **out)
+
+    # Adam trajectory: 4 steps in eval-mode BN (steady state, F5) + 2 steps train-mode, B=8
+    torch.manual_seed(5)
+    model = ref_shim.make_eegnet_tor(ns, 5)
+    xs, ys = GI.adam6_inputs()
+    out = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    out["input_checksum"] = GI.checksum(xs.numpy(), ys.numpy())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    losses, masks1, masks2 = [], [], []
+    for i in range(6):
+        model.train(i < 2)
+        if i < 2:
+            torch.manual_seed(200 + i)
+            masks1.append(torch.empty(8, 64, 1, 125).bernoulli_(0.5).numpy().astype(np.uint8))
+            masks2.append(torch.empty(8, 64, 1, 15).bernoulli_(0.5).numpy().astype(np.uint8))
+            torch.manual_seed(200 + i)
+        loss = crit(model(xs[i]), ys[i])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    out["losses"] = np.array(losses)
+    out["masks1"], out["masks2"] = np.stack(masks1), np.stack(masks2)
+    for k, v in model.state_dict().items():
+        out[f"final::{k}"] = v.detach().numpy().copy()
+    save("eegnet_tor_adam6.npz", **out)
+
+    # Trainer_uni.train(): 3 epochs, N_train=40, N_test=16, bs=16 -- per-step loss + val loss/acc
+    torch.manual_seed(9)
+    model = ref_shim.make_eegnet_tor(ns, 5)
+    trx, try_, tex, tey = GI.trainer_inputs()
+    out = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    out["input_checksum"] = GI.checksum(trx, try_, tex, tey)
+    trainer = M.Trainer_uni(model, [trx, try_, tex, tey], lr=1e-3, batch_size=16, num_epochs=3,
+                            device=torch.device("cpu"))
+    crit0 = trainer.criterion
+    step_losses = []
+
+    class Rec(torch.nn.Module):
+        def forward(self, s, t):
+            l = crit0(s, t)
+            step_losses.append((float(l.detach()), bool(torch.is_grad_enabled())))
+            return l
+    trainer.criterion = Rec()
+    torch.manual_seed(77)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        trainer.train()
+    out["train_step_loss"] = np.array([l for l, ge in step_losses if ge])
+    out["val_batch_loss"] = np.array([l for l, ge in step_losses if not ge])
+    out["stdout"] = np.array(buf.getvalue())
+    for k, v in model.state_dict().items():
+        out[f"final::{k}"] = v.detach().numpy().copy()
+    save("trainer_uni_3ep.npz", **out)
+
+
+def gen_cnn_eeg(ns):
+    import eegnet_oracle as EO
+    C = ns.CNN_EEG
+    for tag, kw, B in (("default", dict(nb_classes=4, Chans=64, Samples=128, dropoutRate=0.25), 8),
+                       ("eav", dict(nb_classes=5, Chans=30, Samples=500, kernLength=300, D=8, F2=64), 4)):
+        torch.manual_seed(4)
+        model = C.EEGNet(**kw)
+        g = torch.Generator().manual_seed(21)
+        with torch.no_grad():
+            for bn in (model.block1[1], model.block1[3], model.block2[2]):
+                bn.weight.copy_(1 + 0.2 * torch.randn(bn.weight.shape, generator=g))
+                bn.bias.copy_(0.1 * torch.randn(bn.bias.shape, generator=g))
+                bn.running_mean.copy_(0.05 * torch.randn(bn.bias.shape, generator=g))
+                bn.running_var.copy_(1 + 0.3 * torch.rand(bn.bias.shape, generator=g))
+        init = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        x = torch.randn(B, kw["Chans"], kw["Samples"], generator=g)    # 3-D input (CNN_EEG.py:60-61)
+        y = torch.randint(0, kw["nb_classes"], (B,), generator=g)
+        out = dict(init, x=x.numpy(), y=y.numpy())
+        crit = torch.nn.CrossEntropyLoss()
+        p_drop = kw.get("dropoutRate", 0.5)
+        F2 = kw.get("F2", 16)
+        DF1 = kw.get("D", 2) * 8
+        T4 = kw["Samples"] // 4
+        for mode in ("train", "eval"):
+            model.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in init.items()})
+            model.train(mode == "train")
+            model.zero_grad()
+            torch.manual_seed(100)
+            if mode == "train":
+                out["mask1"] = torch.empty(B, DF1, 1, T4).bernoulli_(1 - p_drop).numpy().astype(np.uint8)
+                out["mask2"] = torch.empty(B, F2, 1, T4 // 8).bernoulli_(1 - p_drop).numpy().astype(np.uint8)
+                torch.manual_seed(100)
+            o = model(x)
+            loss = crit(o, y)
+            loss.backward()
+            out[f"{mode}::logits"] = o.detach().numpy()
+            out[f"{mode}::loss"] = np.array(loss.item(), dtype=np.float64)
+            for k, v in grads_of(model, EO.CNN_PARAMS).items():
+                out[f"{mode}::{k}"] = v
+            for k, v in model.state_dict().items():
+                if "running" in k or "num_batches" in k:
+                    out[f"{mode}::after::{k}"] = v.detach().numpy().copy()
+        save(f"cnn_eeg_{tag}.npz", **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_shim.load()
+    torch.set_num_threads(8)
+    gen_preproc(ns)
+    gen_eegnet_tor(ns)
+    gen_cnn_eeg(ns)
