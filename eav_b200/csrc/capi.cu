@@ -1,0 +1,241 @@
+// C ABI of libeav_b200.so for the EEGNet path: argument validation, parameter/workspace
+// layout and the launch sequences of forward and backward (include/eav_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "eegnet_kernels.cuh"
+
+namespace eav {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int make_dims(const eav_eegnet_cfg *c, NetDims *d) {
+    EAV_REQUIRE(c != nullptr, EAV_ERR_BAD_ARG, "cfg is NULL");
+    EAV_REQUIRE(c->n_models > 0 && c->batch > 0, EAV_ERR_BAD_ARG, "n_models=%d batch=%d must be positive", c->n_models, c->batch);
+    EAV_REQUIRE(c->chans > 0 && c->samples > 0 && c->kern_len > 0 && c->F1 > 0 && c->D > 0 && c->F2 > 0 &&
+                    c->kern_len2 > 0 && c->pool1 > 0 && c->pool2 > 0 && c->n_classes > 0,
+                EAV_ERR_BAD_ARG, "all model dimensions must be positive");
+    EAV_REQUIRE(c->variant == EAV_VARIANT_TOR || c->variant == EAV_VARIANT_CNN, EAV_ERR_BAD_ARG, "unknown variant %d", c->variant);
+    EAV_REQUIRE(c->dropout_mode >= 0 && c->dropout_mode <= 2, EAV_ERR_BAD_ARG, "unknown dropout_mode %d", c->dropout_mode);
+    EAV_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, EAV_ERR_BAD_ARG, "dropout_p=%f out of [0,1]", c->dropout_p);
+    EAV_REQUIRE((int64_t)c->n_models * c->batch < (1ll << 24), EAV_ERR_UNSUPPORTED, "n_models*batch too large");
+    d->M = c->n_models; d->B = c->batch; d->N = d->M * d->B;
+    d->C = c->chans; d->T = c->samples; d->K1 = c->kern_len; d->F1 = c->F1; d->D = c->D; d->G = c->F1 * c->D;
+    d->F2 = c->F2; d->K2 = c->kern_len2; d->P1 = c->pool1; d->P2 = c->pool2;
+    d->T4 = d->T / d->P1; d->T32 = d->T4 / d->P2; d->NC = c->n_classes; d->FEAT = d->F2 * d->T32;
+    EAV_REQUIRE(d->T32 > 0, EAV_ERR_BAD_ARG, "Samples=%d too short for the two pooling stages", d->T);
+    d->variant = c->variant; d->bn_train = c->bn_train != 0; d->dropout_mode = c->dropout_mode;
+    d->pad1l = (d->K1 - 1) / 2; d->pad2l = (d->K2 - 1) / 2;   // torch padding='same': left = total//2
+    d->p_drop = c->dropout_p; d->eps = c->bn_eps; d->momentum = c->bn_momentum; d->norm_rate = c->norm_rate;
+    d->seed = c->seed; d->step = c->step;
+    if (d->p_drop == 0.f) d->dropout_mode = EAV_DROPOUT_NONE;
+    int64_t o = 0;
+    d->oW1 = o; o += (int64_t)d->F1 * d->K1;
+    d->og1 = o; o += d->F1;
+    d->ob1 = o; o += d->F1;
+    d->oW2 = o; o += (int64_t)d->G * d->C;
+    d->og2 = o; o += d->G;
+    d->ob2 = o; o += d->G;
+    if (d->variant == EAV_VARIANT_TOR) {
+        d->oW3 = o; o += (int64_t)d->F2 * d->G * d->K2;
+        d->oW3p = -1;
+    } else {
+        d->oW3 = o; o += (int64_t)d->G * d->K2;          // depthwise temporal (G,1,1,K2)
+        d->oW3p = o; o += (int64_t)d->F2 * d->G;         // pointwise (F2,G,1,1)
+    }
+    d->og3 = o; o += d->F2;
+    d->ob3 = o; o += d->F2;
+    d->oWd = o; o += (int64_t)d->NC * d->FEAT;
+    d->obd = o; o += d->NC;
+    d->n_params = o;
+    d->pstride = c->param_stride;
+    d->bnstride = c->bn_stride;
+    EAV_REQUIRE(d->pstride >= d->n_params, EAV_ERR_BAD_ARG, "param_stride=%lld < n_params=%lld", (long long)d->pstride, (long long)d->n_params);
+    int64_t b = 0;
+    d->orm1 = b; b += d->F1; d->orv1 = b; b += d->F1;
+    d->orm2 = b; b += d->G;  d->orv2 = b; b += d->G;
+    d->orm3 = b; b += d->F2; d->orv3 = b; b += d->F2;
+    EAV_REQUIRE(d->bnstride >= b, EAV_ERR_BAD_ARG, "bn_stride=%lld < %lld", (long long)d->bnstride, (long long)b);
+    return 0;
+}
+
+static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
+
+WsLayout make_ws_layout(const NetDims &d) {
+    WsLayout w;
+    size_t o = 0;
+    auto take = [&](size_t n_floats) { size_t at = o; o = align_up(o + n_floats * sizeof(float), 256); return at; };
+    const size_t N = d.N;
+    w.y1 = take(N * d.F1 * d.C * d.T);
+    w.y2 = take(N * d.G * d.T);
+    w.d1 = take(N * d.G * d.T4);
+    w.y3d = take(d.variant == EAV_VARIANT_CNN ? N * d.G * d.T4 : 0);
+    w.y3 = take(N * d.F2 * d.T4);
+    w.feat = take(N * d.FEAT);
+    w.probs = take(N * d.NC);
+    w.dz = take(N * d.NC);
+    w.bnf1 = take((size_t)d.M * d.F1 * 4); w.bnf2 = take((size_t)d.M * d.G * 4); w.bnf3 = take((size_t)d.M * d.F2 * 4);
+    w.bnb1 = take((size_t)d.M * d.F1 * 4); w.bnb2 = take((size_t)d.M * d.G * 4); w.bnb3 = take((size_t)d.M * d.F2 * 4);
+    // BN partial sums (largest user)
+    size_t pa = 0;
+    pa = max_sz(pa, N * cdiv(d.C, 4) * cdiv(d.T, 512) * 2 * d.F1);        // tconv_fwd
+    pa = max_sz(pa, N * cdiv(d.T, 128) * 2 * d.G);                        // dw_fwd
+    pa = max_sz(pa, (size_t)d.M * cdiv(d.B, 2) * cdiv(d.T4, 128) * 2 * d.F2);  // sepconv_fwd
+    pa = max_sz(pa, N * 2 * d.F2);                                        // pw_fwd / tail_bwd
+    pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
+    pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
+    w.part = take(pa);
+    // weight-gradient partials (largest user)
+    size_t pb = 0;
+    pb = max_sz(pb, N * d.G * d.C);                                       // dw_bwd
+    pb = max_sz(pb, (size_t)d.M * tconv_dw_ctas_per_model(d) * d.F1 * d.K1);  // tconv_bwd_dw
+    if (d.variant == EAV_VARIANT_TOR) pb = max_sz(pb, (size_t)d.M * sepconv_dw_splits(d) * d.F2 * d.G * 16);
+    else pb = max_sz(pb, max_sz(N * d.F2 * d.G, N * d.G * d.K2));
+    w.partw = take(pb);
+    w.dz3 = take(N * d.F2 * d.T4);
+    w.dd1 = take(N * d.G * d.T4);
+    w.dy3d = take(d.variant == EAV_VARIANT_CNN ? N * d.G * d.T4 : 0);
+    w.dz2 = take(N * d.G * d.T);
+    w.dz1 = take(N * d.F1 * d.C * d.T);
+    w.total = o;
+    return w;
+}
+
+}  // namespace eav
+
+using namespace eav;
+
+extern "C" const char *eav_last_error_string(void) { return g_err; }
+extern "C" int eav_abi_version(void) { return EAV_ABI_VERSION; }
+
+extern "C" int eav_check_device(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("no CUDA device: %s", cudaGetErrorString(e)); return (int)e; }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    EAV_REQUIRE(major == 10, EAV_ERR_UNSUPPORTED, "device is sm_%d%d; libeav_b200 is built for sm_100a only", major, minor);
+    return 0;
+}
+
+extern "C" int64_t eav_eegnet_param_layout(const eav_eegnet_cfg *cfg, int64_t *offsets) {
+    if (cfg == nullptr) { set_error("cfg is NULL"); return EAV_ERR_BAD_ARG; }
+    eav_eegnet_cfg c = *cfg;
+    c.param_stride = INT32_MAX;   // layout query: strides not checked
+    c.bn_stride = INT32_MAX;
+    NetDims d;
+    int rc = make_dims(&c, &d);
+    if (rc) return rc;
+    if (offsets) {
+        if (d.variant == EAV_VARIANT_TOR) {
+            int64_t o[12] = {d.oW1, d.og1, d.ob1, d.oW2, d.og2, d.ob2, d.oW3, d.og3, d.ob3, d.oWd, d.obd, -1};
+            memcpy(offsets, o, sizeof(o));
+        } else {
+            int64_t o[12] = {d.oW1, d.og1, d.ob1, d.oW2, d.og2, d.ob2, d.oW3, d.oW3p, d.og3, d.ob3, d.oWd, d.obd};
+            memcpy(offsets, o, sizeof(o));
+        }
+    }
+    return d.n_params;
+}
+
+extern "C" size_t eav_eegnet_workspace_bytes(const eav_eegnet_cfg *cfg) {
+    NetDims d;
+    if (make_dims(cfg, &d)) return 0;
+    return make_ws_layout(d).total;
+}
+
+extern "C" int eav_eegnet_workspace_offsets(const eav_eegnet_cfg *cfg, size_t *o) {
+    NetDims d;
+    int rc = make_dims(cfg, &d);
+    if (rc) return rc;
+    EAV_REQUIRE(o != nullptr, EAV_ERR_BAD_ARG, "workspace_offsets: null pointer");
+    const WsLayout w = make_ws_layout(d);
+    const size_t v[16] = {w.y1, w.y2, w.d1, w.y3d, w.y3, w.feat, w.probs, w.dz, w.dz3, w.dd1, w.dy3d, w.dz2, w.dz1,
+                          w.bnf1, w.bnf2, w.bnf3};
+    memcpy(o, v, sizeof(v));
+    return 0;
+}
+
+#define WS(T, off) reinterpret_cast<T *>(reinterpret_cast<char *>(workspace) + (off))
+#define TRY(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
+
+extern "C" int eav_eegnet_forward(const eav_eegnet_cfg *cfg, const float *x, const int32_t *x_index, float *params,
+                                  float *bn_state, const uint8_t *mask1, const uint8_t *mask2, float *out,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    NetDims d;
+    TRY(make_dims(cfg, &d));
+    EAV_REQUIRE(x && params && bn_state && out && workspace, EAV_ERR_BAD_ARG, "eegnet_forward: null pointer");
+    const WsLayout w = make_ws_layout(d);
+    EAV_REQUIRE(workspace_bytes >= w.total, EAV_ERR_WORKSPACE, "eegnet_forward: workspace %zu < required %zu", workspace_bytes, w.total);
+    EAV_REQUIRE(d.dropout_mode != EAV_DROPOUT_MASK || (mask1 && mask2), EAV_ERR_BAD_ARG, "eegnet_forward: dropout masks required");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *part = WS(float, w.part);
+    float *pstat = d.bn_train ? part : nullptr;
+    int rows = 0;
+
+    TRY(launch_tconv_fwd(d, x, x_index, params, WS(float, w.y1), pstat, &rows, st));
+    TRY(launch_bn_finalize(d, 1, part, rows, (double)d.B * d.C * d.T, params, bn_state, WS(float4, w.bnf1), st));
+    TRY(launch_dw_fwd(d, WS(float, w.y1), params, WS(float4, w.bnf1), WS(float, w.y2), pstat, &rows, st));
+    if (d.variant == EAV_VARIANT_TOR && d.norm_rate > 0.f)   // hook after the layer used W_old (EEGNet_tor.py:33-34)
+        TRY(launch_renorm_rows(params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st));
+    TRY(launch_bn_finalize(d, 2, part, rows, (double)d.B * d.T, params, bn_state, WS(float4, w.bnf2), st));
+    TRY(launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), mask1, WS(float, w.d1), st));
+    if (d.variant == EAV_VARIANT_TOR) {
+        TRY(launch_sepconv_fwd(d, WS(float, w.d1), params, WS(float, w.y3), pstat, &rows, st));
+    } else {
+        TRY(launch_dwt_fwd(d, WS(float, w.d1), params, WS(float, w.y3d), st));
+        TRY(launch_pw_fwd(d, WS(float, w.y3d), params, WS(float, w.y3), pstat, &rows, st));
+    }
+    TRY(launch_bn_finalize(d, 3, part, rows, (double)d.B * d.T4, params, bn_state, WS(float4, w.bnf3), st));
+    TRY(launch_tail_fwd(d, WS(float, w.y3), WS(float4, w.bnf3), mask2, params, WS(float, w.feat), out,
+                        WS(float, w.probs), st));
+    if (d.variant == EAV_VARIANT_TOR && d.norm_rate > 0.f)   // hook on dense (EEGNet_tor.py:47-48)
+        TRY(launch_renorm_rows(params + d.oWd, (int64_t)d.M * d.NC, d.FEAT, d.FEAT, d.NC, d.pstride, d.norm_rate, st));
+    return 0;
+}
+
+extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, const int32_t *x_index,
+                                   const float *params, const float *dout, const uint8_t *mask1,
+                                   const uint8_t *mask2, float *grads, void *workspace, size_t workspace_bytes,
+                                   void *stream) {
+    NetDims d;
+    TRY(make_dims(cfg, &d));
+    EAV_REQUIRE(x && params && dout && grads && workspace, EAV_ERR_BAD_ARG, "eegnet_backward: null pointer");
+    const WsLayout w = make_ws_layout(d);
+    EAV_REQUIRE(workspace_bytes >= w.total, EAV_ERR_WORKSPACE, "eegnet_backward: workspace %zu < required %zu", workspace_bytes, w.total);
+    EAV_REQUIRE(d.dropout_mode != EAV_DROPOUT_MASK || (mask1 && mask2), EAV_ERR_BAD_ARG, "eegnet_backward: dropout masks required");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *part = WS(float, w.part);
+    float *partw = WS(float, w.partw);
+
+    TRY(launch_tail_bwd(d, dout, WS(float, w.probs), params, WS(float, w.y3), WS(float4, w.bnf3), mask2,
+                        WS(float, w.dz), WS(float, w.dz3), part, st));
+    TRY(launch_dense_bwd_w(d, WS(float, w.feat), WS(float, w.dz), grads, st));
+    TRY(launch_bn_bwd_finalize(d, 3, part, d.B, (double)d.B * d.T4, params, WS(float4, w.bnf3), WS(float4, w.bnb3), grads, st));
+    if (d.variant == EAV_VARIANT_TOR) {
+        TRY(launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), params,
+                                  WS(float, w.dd1), st));
+        TRY(launch_sepconv_bwd_dw(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
+                                  WS(float, w.d1), partw, grads, st));
+    } else {
+        TRY(launch_pw_bwd(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), WS(float, w.y3d),
+                          params, WS(float, w.dy3d), partw, grads, st));
+        TRY(launch_dwt_bwd(d, WS(float, w.dy3d), WS(float, w.d1), params, WS(float, w.dd1), partw, grads, st));
+    }
+    TRY(launch_pool1_bwd(d, WS(float, w.dd1), WS(float, w.y2), WS(float4, w.bnf2), mask1, WS(float, w.dz2), part, st));
+    TRY(launch_bn_bwd_finalize(d, 2, part, d.B, (double)d.B * d.T, params, WS(float4, w.bnf2), WS(float4, w.bnb2), grads, st));
+    TRY(launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
+                      WS(float4, w.bnf1), params, WS(float, w.dz1), partw, part, grads, st));
+    TRY(launch_bn_bwd_finalize(d, 1, part, d.B, (double)d.B * d.C * d.T, params, WS(float4, w.bnf1), WS(float4, w.bnb1), grads, st));
+    TRY(launch_tconv_bwd_dw(d, x, x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
+                            partw, grads, st));
+    return 0;
+}

@@ -1,0 +1,745 @@
+// Backward kernels of the EEGNet path for sm_100a: the gradient of
+// CNN_torch/EEGNet_tor.py:50-67 (and CNN_torch/CNN_EEG.py:57-67) w.r.t. all 11 (12)
+// parameter tensors.  BatchNorm backward is split the usual way: producers emit
+// dz = dL/d(BN output) together with per-row partial sums (sum dz, sum dz*xhat);
+// bn_bwd_finalize turns them into {k, c1, c2}; consumers rebuild
+//     dL/d(BN input) = k * (dz - c1 - xhat * c2)        (c1 = c2 = 0 in eval mode)
+// on the fly while staging their tiles.  All reductions are two-stage and ordered, so
+// results are deterministic run to run.
+#include "eegnet_kernels.cuh"
+
+namespace eav {
+
+// =================================================================================
+// Tail backward: softmax Jacobian (variant 0), dense input gradient (with the
+// re-normed weight), dropout, AvgPool(1,P2), ELU' -> dz3 + BN3 partials.
+// =================================================================================
+__global__ void __launch_bounds__(128)
+tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
+                const float *__restrict__ params, int64_t pstride, int64_t oWd, const float *__restrict__ y3,
+                const float4 *__restrict__ bn3, const uint8_t *__restrict__ mask2, int B, int F2, int T4,
+                int T32, int P2, int NC, int softmax_out, int dropout_mode, float p_drop, uint64_t seed,
+                uint64_t step, float *__restrict__ dz, float *__restrict__ dz3, float *__restrict__ part) {
+    extern __shared__ float sm[];  // dfeat_s[FEAT] + dz_s[NC]
+    const int FEAT = F2 * T32;
+    float *dfeat_s = sm, *dz_s = sm + FEAT;
+    const int n = blockIdx.x, m = n / B, tid = threadIdx.x;
+    if (tid == 0) {
+        if (softmax_out) {
+            float dot = 0.f;
+            for (int j = 0; j < NC; ++j) dot = fmaf(dout[(int64_t)n * NC + j], probs[(int64_t)n * NC + j], dot);
+            for (int j = 0; j < NC; ++j) {
+                float v = probs[(int64_t)n * NC + j] * (dout[(int64_t)n * NC + j] - dot);
+                dz_s[j] = v;
+                dz[(int64_t)n * NC + j] = v;
+            }
+        } else {
+            for (int j = 0; j < NC; ++j) {
+                float v = dout[(int64_t)n * NC + j];
+                dz_s[j] = v;
+                dz[(int64_t)n * NC + j] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
+    const float *Wd = params + (int64_t)m * pstride + oWd;
+    for (int i = tid; i < FEAT; i += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < NC; ++j) s = fmaf(Wd[(int64_t)j * FEAT + i], dz_s[j], s);
+        int64_t e = (int64_t)n * FEAT + i;
+        if (dropout_mode == EAV_DROPOUT_MASK) s = mask2[e] ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 2u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        dfeat_s[i] = s * (1.f / (float)P2);
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int o = warp; o < F2; o += blockDim.x >> 5) {
+        const float4 st = bn3[(int64_t)m * F2 + o];
+        const float *src = y3 + ((int64_t)n * F2 + o) * T4;
+        float *dst = dz3 + ((int64_t)n * F2 + o) * T4;
+        float s1 = 0.f, s2 = 0.f;
+        for (int u = lane; u < T4; u += 32) {
+            int v = u / P2;
+            float y = src[u];
+            float g = (v < T32) ? dfeat_s[o * T32 + v] * elu_grad_from_pre(fmaf(y, st.z, st.w)) : 0.f;
+            dst[u] = g;
+            s1 += g;
+            s2 = fmaf(g, (y - st.x) * st.y, s2);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            part[((int64_t)n * F2 + o) * 2] = s1;
+            part[((int64_t)n * F2 + o) * 2 + 1] = s2;
+        }
+    }
+}
+
+int launch_tail_bwd(const NetDims &d, const float *dout, const float *probs, const float *params,
+                    const float *y3, const float4 *bn3, const uint8_t *mask2, float *dz, float *dz3,
+                    float *part, cudaStream_t st) {
+    size_t smem = (size_t)(d.FEAT + d.NC) * sizeof(float);
+    tail_bwd_kernel<<<d.N, 128, smem, st>>>(dout, probs, params, d.pstride, d.oWd, y3, bn3, mask2, d.B, d.F2,
+                                            d.T4, d.T32, d.P2, d.NC, d.variant == EAV_VARIANT_TOR,
+                                            d.dropout_mode, d.p_drop, d.seed, d.step, dz, dz3, part);
+    EAV_CUDA_LAUNCH_CHECK("tail_bwd");
+    return 0;
+}
+
+// dWd[m,j,i] = sum_b dz[n,j] * feat[n,i];  dbd[m,j] = sum_b dz[n,j]
+__global__ void dense_bwd_w_kernel(const float *__restrict__ feat, const float *__restrict__ dz, int B,
+                                   int FEAT, int NC, int64_t pstride, int64_t oWd, int64_t obd,
+                                   float *__restrict__ grads) {
+    const int m = blockIdx.z, j = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < FEAT) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) {
+            int64_t n = (int64_t)m * B + b;
+            s = fmaf(dz[n * NC + j], feat[n * FEAT + i], s);
+        }
+        grads[(int64_t)m * pstride + oWd + (int64_t)j * FEAT + i] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += dz[((int64_t)m * B + b) * NC + j];
+        grads[(int64_t)m * pstride + obd + j] = s;
+    }
+}
+
+int launch_dense_bwd_w(const NetDims &d, const float *feat, const float *dz, float *grads, cudaStream_t st) {
+    dense_bwd_w_kernel<<<dim3(cdiv(d.FEAT, 128), d.NC, d.M), 128, 0, st>>>(feat, dz, d.B, d.FEAT, d.NC, d.pstride,
+                                                                          d.oWd, d.obd, grads);
+    EAV_CUDA_LAUNCH_CHECK("dense_bwd_w");
+    return 0;
+}
+
+// =================================================================================
+// BatchNorm backward statistics.  part: [M][rows_per_model][ch][2] = (sum dz, sum dz*xhat).
+// Writes d(gamma) = sum dz*xhat, d(beta) = sum dz and the {k, c1, c2} block.
+// =================================================================================
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ part, int rows_per_model, int ch,
+                                       double count, const float *__restrict__ params, int64_t pstride,
+                                       int64_t og, int64_t ob, const float4 *__restrict__ bnf, int bn_train,
+                                       float4 *__restrict__ bnb, float *__restrict__ grads) {
+    const int c = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
+    for (int r = lane; r < rows_per_model; r += 32) {
+        s1 += (double)p[((int64_t)r * ch + c) * 2];
+        s2 += (double)p[((int64_t)r * ch + c) * 2 + 1];
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) {
+        grads[(int64_t)m * pstride + og + c] = (float)s2;
+        grads[(int64_t)m * pstride + ob + c] = (float)s1;
+        float k = params[(int64_t)m * pstride + og + c] * bnf[(int64_t)m * ch + c].y;
+        float c1 = bn_train ? (float)(s1 / count) : 0.f;
+        float c2 = bn_train ? (float)(s2 / count) : 0.f;
+        bnb[(int64_t)m * ch + c] = make_float4(k, c1, c2, 0.f);
+    }
+}
+
+int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
+                           double count, const float *params, const float4 *bnf, float4 *bnb,
+                           float *grads, cudaStream_t st) {
+    int ch;
+    int64_t og, ob;
+    if (layer == 1) { ch = d.F1; og = d.og1; ob = d.ob1; }
+    else if (layer == 2) { ch = d.G; og = d.og2; ob = d.ob2; }
+    else { ch = d.F2; og = d.og3; ob = d.ob3; }
+    bn_bwd_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, params, d.pstride, og,
+                                                         ob, bnf, d.bn_train, bnb, grads);
+    EAV_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
+    return 0;
+}
+
+// =================================================================================
+// M6 weight gradient:  dW3[m,o,g,k] = sum_{b,u} dy3[n,o,u] * d1[n,g,u+k-7]
+// GEMM view M=F2, N=G*16, K=B*T4.  CTA = (model, 16 input channels, sample split);
+// thread = 8 o x 8 k, walking u four at a time (8 broadcast LDS.128 + 3 LDS.128 per
+// 256 FFMA).  Split partials are reduced by reduce_partials in a fixed order.
+// =================================================================================
+constexpr int SW_GC = 16;       // input channels per CTA
+constexpr int SW_UP = 128;      // padded positions (T4 <= 128 per pass)
+constexpr int SW_XS = 148;      // d1 row: 7 left pad + 128 + right pad (>= 128+15+4)
+
+__global__ void __launch_bounds__(256, 2)
+sepconv_bwd_dw_kernel(const float *__restrict__ dz3, const float *__restrict__ y3,
+                      const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
+                      const float *__restrict__ d1, int B, int F2, int G, int L, int padl, int splits,
+                      float *__restrict__ part) {
+    extern __shared__ __align__(16) float smem[];
+    float *dys = smem;                 // [F2][SW_UP]
+    float *xs = smem + F2 * SW_UP;     // [SW_GC][SW_XS]
+    const int m = blockIdx.z, split = blockIdx.y, g0 = blockIdx.x * SW_GC;
+    const int tid = threadIdx.x;
+    const int kq = tid & 1, gl = (tid >> 1) & (SW_GC - 1), og = tid >> 5;  // og: group of 8 output channels
+    const int b_lo = (int)((int64_t)B * split / splits), b_hi = (int)((int64_t)B * (split + 1) / splits);
+    const int n_og = F2 / 8;  // output-channel groups; threads with og >= n_og idle (F2 <= 64)
+
+    float acc[8][8];
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) acc[oo][kk] = 0.f;
+
+    for (int b = b_lo; b < b_hi; ++b) {
+        const int64_t n = (int64_t)m * B + b;
+        for (int u_base = 0; u_base < L; u_base += SW_UP) {
+            __syncthreads();
+            for (int i = tid; i < F2 * SW_UP; i += 256) {
+                int o = i / SW_UP, j = i - o * SW_UP;
+                int u = u_base + j;
+                float v = 0.f;
+                if (u < L) {
+                    int64_t idx = (n * F2 + o) * (int64_t)L + u;
+                    v = dz3[idx];
+                    const float4 kb = bnb[(int64_t)m * F2 + o];
+                    if (bn_train) {
+                        const float4 kf = bnf[(int64_t)m * F2 + o];
+                        v = kb.x * (v - kb.y - (y3[idx] - kf.x) * kf.y * kb.z);
+                    } else {
+                        v = kb.x * v;
+                    }
+                }
+                dys[i] = v;
+            }
+            for (int i = tid; i < SW_GC * SW_XS; i += 256) {
+                int gg = i / SW_XS, j = i - gg * SW_XS;
+                int u = u_base - padl + j;
+                float v = 0.f;
+                if (g0 + gg < G && u >= 0 && u < L) v = d1[(n * G + g0 + gg) * (int64_t)L + u];
+                xs[i] = v;
+            }
+            __syncthreads();
+            if (og < n_og) {
+                const float *dr = dys + og * 8 * SW_UP;
+                const float *xr = xs + gl * SW_XS + 8 * kq;
+#pragma unroll 2
+                for (int u = 0; u < SW_UP; u += 4) {
+                    float xw[12];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        float4 v = *reinterpret_cast<const float4 *>(xr + u + 4 * q);
+                        xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int oo = 0; oo < 8; ++oo) {
+                        float4 d4 = *reinterpret_cast<const float4 *>(dr + oo * SW_UP + u);
+                        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu)
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                acc[oo][kk] = fmaf(dv[uu], xw[uu + kk], acc[oo][kk]);
+                    }
+                }
+            }
+        }
+    }
+    if (og < n_og && g0 + gl < G) {
+        // part[m][split][o][g][k]
+        float *dst = part + (((int64_t)m * splits + split) * F2) * (int64_t)G * 16;
+#pragma unroll
+        for (int oo = 0; oo < 8; ++oo) {
+            float *p = dst + (((int64_t)(og * 8 + oo)) * G + g0 + gl) * 16 + 8 * kq;
+            reinterpret_cast<float4 *>(p)[0] = make_float4(acc[oo][0], acc[oo][1], acc[oo][2], acc[oo][3]);
+            reinterpret_cast<float4 *>(p)[1] = make_float4(acc[oo][4], acc[oo][5], acc[oo][6], acc[oo][7]);
+        }
+    }
+}
+
+int sepconv_dw_splits(const NetDims &d) {
+    // aim for >= ~4 waves of CTAs on 148 SMs x 2 resident, never more splits than samples
+    int per_model = cdiv(d.G, SW_GC);
+    int want = cdiv(148 * 2 * 3, d.M * per_model);
+    int s = want < 1 ? 1 : want;
+    if (s > d.B) s = d.B;
+    if (s > 64) s = 64;
+    return s;
+}
+
+int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                          const float4 *bnb3, const float *d1, float *part, float *grads, cudaStream_t st) {
+    EAV_REQUIRE(d.F2 % 8 == 0 && d.F2 <= 64, EAV_ERR_UNSUPPORTED, "sepconv_dw: F2=%d unsupported (multiple of 8, <= 64)", d.F2);
+    EAV_REQUIRE(d.K2 == 16, EAV_ERR_UNSUPPORTED, "sepconv_dw: kernel length %d unsupported", d.K2);
+    const int splits = sepconv_dw_splits(d);
+    size_t smem = (size_t)(d.F2 * SW_UP + SW_GC * SW_XS) * sizeof(float);
+    dim3 grid(cdiv(d.G, SW_GC), splits, d.M);
+    sepconv_bwd_dw_kernel<<<grid, 256, smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, d1, d.B, d.F2, d.G, d.T4,
+                                                   d.pad2l, splits, part);
+    EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dw");
+    return launch_reduce_partials(part, splits, (int64_t)d.F2 * d.G * 16, d.M, d.pstride, grads + d.oW3, st);
+}
+
+// dst[m][i] = sum_j part[m][j][i]  (fixed order)
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int n_part, int64_t len,
+                                       int64_t dst_stride, float *__restrict__ dst) {
+    const int m = blockIdx.y;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const float *p = part + (int64_t)m * n_part * len + i;
+        float s = 0.f;
+        for (int j = 0; j < n_part; ++j) s += p[(int64_t)j * len];
+        dst[(int64_t)m * dst_stride + i] = s;
+    }
+}
+
+int launch_reduce_partials(const float *part, int n_part, int64_t len, int n_models, int64_t dst_stride,
+                           float *dst, cudaStream_t st) {
+    int bx = (int)std::min<int64_t>(cdiv64(len, 256), 1024);
+    reduce_partials_kernel<<<dim3(bx, n_models), 256, 0, st>>>(part, n_part, len, dst_stride, dst);
+    EAV_CUDA_LAUNCH_CHECK("reduce_partials");
+    return 0;
+}
+
+// =================================================================================
+// Variant 1 block-2 backward: pointwise conv then depthwise temporal conv.
+// =================================================================================
+// dy3d[n,g,u] = sum_o W3p[o,g] * dy3[n,o,u];   per-sample partial dW3p[n][o][g] = sum_u dy3[n,o,u]*y3d[n,g,u]
+__global__ void __launch_bounds__(128)
+pw_bwd_kernel(const float *__restrict__ dz3, const float *__restrict__ y3, const float4 *__restrict__ bnf,
+              const float4 *__restrict__ bnb, int bn_train, const float *__restrict__ y3d,
+              const float *__restrict__ params, int64_t pstride, int64_t oW3p, int B, int G, int F2, int L,
+              float *__restrict__ dy3d, float *__restrict__ part) {
+    extern __shared__ float sm[];   // dys[F2][L] + w[F2][G]
+    float *dys = sm, *wsh = sm + F2 * L;
+    const int n = blockIdx.x, m = n / B, tid = threadIdx.x;
+    for (int i = tid; i < F2 * L; i += blockDim.x) {
+        int o = i / L;
+        int64_t idx = (int64_t)n * F2 * L + i;
+        float v = dz3[idx];
+        const float4 kb = bnb[(int64_t)m * F2 + o];
+        if (bn_train) {
+            const float4 kf = bnf[(int64_t)m * F2 + o];
+            v = kb.x * (v - kb.y - (y3[idx] - kf.x) * kf.y * kb.z);
+        } else {
+            v = kb.x * v;
+        }
+        dys[i] = v;
+    }
+    const float *W = params + (int64_t)m * pstride + oW3p;
+    for (int i = tid; i < F2 * G; i += blockDim.x) wsh[i] = W[i];
+    __syncthreads();
+    for (int i = tid; i < G * L; i += blockDim.x) {
+        int g = i / L, u = i - g * L;
+        float s = 0.f;
+        for (int o = 0; o < F2; ++o) s = fmaf(wsh[o * G + g], dys[o * L + u], s);
+        dy3d[(int64_t)n * G * L + i] = s;
+    }
+    for (int i = tid; i < F2 * G; i += blockDim.x) {
+        int o = i / G, g = i - o * G;
+        const float *a = y3d + ((int64_t)n * G + g) * L;
+        float s = 0.f;
+        for (int u = 0; u < L; ++u) s = fmaf(dys[o * L + u], a[u], s);
+        part[(int64_t)n * F2 * G + i] = s;
+    }
+}
+
+int launch_pw_bwd(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                  const float4 *bnb3, const float *y3d, const float *params, float *dy3d, float *part,
+                  float *grads, cudaStream_t st) {
+    size_t smem = (size_t)(d.F2 * d.T4 + d.F2 * d.G) * sizeof(float);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "pw_bwd: F2*T4 too large");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(pw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    pw_bwd_kernel<<<d.N, 128, smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, y3d, params, d.pstride, d.oW3p, d.B,
+                                          d.G, d.F2, d.T4, dy3d, part);
+    EAV_CUDA_LAUNCH_CHECK("pw_bwd");
+    return launch_reduce_partials(part, d.B, (int64_t)d.F2 * d.G, d.M, d.pstride, grads + d.oW3p, st);
+}
+
+// dd1[n,g,u'] = sum_k W3d[g,k] * dy3d[n,g,u'-k+padl];  per-sample dW3d[n][g][k] = sum_u dy3d[n,g,u]*d1[n,g,u+k-padl]
+__global__ void __launch_bounds__(128)
+dwt_bwd_kernel(const float *__restrict__ dy3d, const float *__restrict__ d1, const float *__restrict__ params,
+               int64_t pstride, int64_t oW3, int B, int G, int L, int K2, int padl, float *__restrict__ dd1,
+               float *__restrict__ part) {
+    const int g = blockIdx.x, n = blockIdx.y, m = n / B;
+    const float *w = params + (int64_t)m * pstride + oW3 + (int64_t)g * K2;
+    const float *dy = dy3d + ((int64_t)n * G + g) * L;
+    const float *x = d1 + ((int64_t)n * G + g) * L;
+    for (int u = threadIdx.x; u < L; u += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < K2; ++k) {
+            int uo = u - k + padl;
+            if (uo >= 0 && uo < L) s = fmaf(w[k], dy[uo], s);
+        }
+        dd1[((int64_t)n * G + g) * L + u] = s;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < K2; k += blockDim.x >> 5) {
+        float s = 0.f;
+        for (int u = lane; u < L; u += 32) {
+            int ui = u + k - padl;
+            if (ui >= 0 && ui < L) s = fmaf(dy[u], x[ui], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) part[((int64_t)n * G + g) * K2 + k] = s;
+    }
+}
+
+int launch_dwt_bwd(const NetDims &d, const float *dy3d, const float *d1, const float *params, float *dd1,
+                   float *part, float *grads, cudaStream_t st) {
+    dwt_bwd_kernel<<<dim3(d.G, d.N), 128, 0, st>>>(dy3d, d1, params, d.pstride, d.oW3, d.B, d.G, d.T4, d.K2,
+                                                   d.pad2l, dd1, part);
+    EAV_CUDA_LAUNCH_CHECK("dwt_bwd");
+    return launch_reduce_partials(part, d.B, (int64_t)d.G * d.K2, d.M, d.pstride, grads + d.oW3, st);
+}
+
+// =================================================================================
+// M5 backward: dropout, AvgPool(1,P1), ELU' -> dz2 + BN2 partials.  One warp per (n,g) row.
+// =================================================================================
+__global__ void __launch_bounds__(256)
+pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, const float4 *__restrict__ bnf2,
+                 const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1, int dropout_mode,
+                 float p_drop, uint64_t seed, uint64_t step, int64_t rows, float *__restrict__ dz2,
+                 float *__restrict__ part) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int g = (int)(row % G), n = (int)(row / G);
+    const float4 st = bnf2[(int64_t)(n / B) * G + g];
+    const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
+    const float sc = inv_keep / (float)P1;
+    float s1 = 0.f, s2 = 0.f;
+    for (int t = lane; t < T; t += 32) {
+        int u = t / P1;
+        float y = y2[row * T + t];
+        float gval = 0.f;
+        if (u < T4) {
+            int64_t e = row * T4 + u;
+            bool keep = true;
+            if (dropout_mode == EAV_DROPOUT_MASK) keep = mask1[e] != 0;
+            else if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep(seed, step, 1u, (uint64_t)e, p_drop);
+            if (keep) gval = dd1[e] * sc * elu_grad_from_pre(fmaf(y, st.z, st.w));
+        }
+        dz2[row * T + t] = gval;
+        s1 += gval;
+        s2 = fmaf(gval, (y - st.x) * st.y, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { part[row * 2] = s1; part[row * 2 + 1] = s2; }
+}
+
+int launch_pool1_bwd(const NetDims &d, const float *dd1, const float *y2, const float4 *bnf2,
+                     const uint8_t *mask1, float *dz2, float *part, cudaStream_t st) {
+    int64_t rows = (int64_t)d.N * d.G;
+    pool1_bwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(dd1, y2, bnf2, mask1, d.B, d.G, d.T, d.T4, d.P1,
+                                                               d.dropout_mode, d.p_drop, d.seed, d.step, rows,
+                                                               dz2, part);
+    EAV_CUDA_LAUNCH_CHECK("pool1_bwd");
+    return 0;
+}
+
+// =================================================================================
+// M4 backward (+ BN2 bwd on load, ELU1', BN1 partials).  CTA = (sample n, temporal filter f):
+//   dW2[fD+d, c] += sum_t dy2[n,fD+d,t] * a1[n,f,c,t]          (per-CTA partial, reduced later)
+//   dz1[n,f,c,t]  = act'(.) * sum_d W2new[fD+d,c] * dy2[n,fD+d,t]
+// a1 = act(BN1(y1)) is recomputed from the saved raw conv output.
+// =================================================================================
+constexpr int DB_THREADS = 256;
+constexpr int DB_TS = 16;   // t-slices for the dW2 reduction
+
+__global__ void __launch_bounds__(DB_THREADS, 2)
+dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const float4 *__restrict__ bnf2,
+              const float4 *__restrict__ bnb2, const float *__restrict__ y1, const float4 *__restrict__ bnf1,
+              const float *__restrict__ params, int64_t pstride, int64_t oW2, int bn_train, int elu1, int B,
+              int F1, int D, int C, int T, float *__restrict__ dz1, float *__restrict__ part_w,
+              float *__restrict__ part_bn) {
+    extern __shared__ __align__(16) float smem[];
+    const int TS = T + 1;                 // a1 row stride (odd-ish => conflict-free column walks)
+    float *a1s = smem;                    // [C][TS]
+    float *dys = a1s + ((C * TS + 3) & ~3);  // [T][DMAXB=8]
+    float *w2s = dys + T * 8;             // [D][C]
+    float *red = w2s + 8 * C;             // [DB_TS][D*C] for the dW2 cross-slice reduction (reuses after phase 1)
+    const int n = blockIdx.x / F1, f = blockIdx.x - n * F1, m = n / B;
+    const int G = F1 * D, tid = threadIdx.x;
+    const float4 s1 = bnf1[(int64_t)m * F1 + f];
+
+    // stage dy2 (BN2 backward applied) as [t][d], W2 slice, and a1
+    for (int i = tid; i < D * T; i += DB_THREADS) {
+        int dd = i / T, t = i - dd * T;
+        int g = f * D + dd;
+        int64_t idx = ((int64_t)n * G + g) * T + t;
+        float v = dz2[idx];
+        const float4 kb = bnb2[(int64_t)m * G + g];
+        if (bn_train) {
+            const float4 kf = bnf2[(int64_t)m * G + g];
+            v = kb.x * (v - kb.y - (y2[idx] - kf.x) * kf.y * kb.z);
+        } else {
+            v = kb.x * v;
+        }
+        dys[t * 8 + dd] = v;
+    }
+    if (D < 8)
+        for (int i = tid; i < T * 8; i += DB_THREADS)
+            if ((i & 7) >= D) dys[i] = 0.f;
+    const float *W2 = params + (int64_t)m * pstride + oW2 + (int64_t)f * D * C;
+    for (int i = tid; i < 8 * C; i += DB_THREADS) w2s[i] = (i < D * C) ? W2[i] : 0.f;
+    const float *y1r = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T;
+    for (int i = tid; i < C * T; i += DB_THREADS) {
+        int c = i / T, t = i - c * T;
+        float v = fmaf(y1r[i], s1.z, s1.w);
+        a1s[c * TS + t] = elu1 ? elu_f(v) : v;
+    }
+    __syncthreads();
+
+    // phase 1: dW2 partial.  work item = (channel pair cp, t-slice ts); 16 accumulators.
+    {
+        const int n_cp = (C + 1) / 2;
+        const int per = ((T + DB_TS - 1) / DB_TS) | 1;   // odd: slices start in different banks
+        for (int item = tid; item < n_cp * DB_TS; item += DB_THREADS) {
+            const int cp = item % n_cp, ts = item / n_cp;
+            float acc[2][8];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) acc[q][dd] = 0.f;
+            const int c0 = 2 * cp, c1 = (2 * cp + 1 < C) ? 2 * cp + 1 : c0;
+            const int t_lo = min(T, ts * per), t_hi = min(T, t_lo + per);
+            for (int t = t_lo; t < t_hi; ++t) {
+                float4 da = *reinterpret_cast<const float4 *>(dys + t * 8);
+                float4 db = *reinterpret_cast<const float4 *>(dys + t * 8 + 4);
+                const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+                float a0 = a1s[c0 * TS + t], a1v = a1s[c1 * TS + t];
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) {
+                    acc[0][dd] = fmaf(dv[dd], a0, acc[0][dd]);
+                    acc[1][dd] = fmaf(dv[dd], a1v, acc[1][dd]);
+                }
+            }
+            // red[ts][dd][c]
+#pragma unroll
+            for (int dd = 0; dd < 8; ++dd) {
+                if (dd < D) {
+                    red[(ts * D + dd) * C + c0] = acc[0][dd];
+                    if (2 * cp + 1 < C) red[(ts * D + dd) * C + c1] = acc[1][dd];
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < D * C; i += DB_THREADS) {
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < DB_TS; ++q) s += red[q * D * C + i];
+            part_w[((int64_t)n * F1 + f) * (D * C) + i] = s;   // [n][f][d][c] == [n][g][c]
+        }
+    }
+
+    // phase 2: dz1 and BN1 partials.  thread per t.
+    float p1 = 0.f, p2 = 0.f;
+    for (int t = tid; t < T; t += DB_THREADS) {
+        float4 da = *reinterpret_cast<const float4 *>(dys + t * 8);
+        float4 db = *reinterpret_cast<const float4 *>(dys + t * 8 + 4);
+        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        for (int c = 0; c < C; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < 8; ++dd) s = fmaf(w2s[dd * C + c], dv[dd], s);   // rows >= D are zero
+            float a = a1s[c * TS + t];
+            float gr = elu1 ? (a > 0.f ? 1.f : a + 1.f) : 1.f;
+            float g = s * gr;
+            int64_t idx = (int64_t)c * T + t;
+            dz1[(((int64_t)n * F1 + f) * C) * (int64_t)T + idx] = g;
+            p1 += g;
+            p2 = fmaf(g, (y1r[idx] - s1.x) * s1.y, p2);
+        }
+    }
+    __shared__ float redb[DB_THREADS / 32][2];
+    p1 = warp_sum(p1);
+    p2 = warp_sum(p2);
+    if ((tid & 31) == 0) { redb[tid >> 5][0] = p1; redb[tid >> 5][1] = p2; }
+    __syncthreads();
+    if (tid < 2) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < DB_THREADS / 32; ++w) s += redb[w][tid];
+        part_bn[((int64_t)n * F1 + f) * 2 + tid] = s;
+    }
+}
+
+int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const float4 *bnf2,
+                  const float4 *bnb2, const float *y1, const float4 *bnf1, const float *params,
+                  float *dz1, float *part_w, float *part_bn, float *grads, cudaStream_t st) {
+    EAV_REQUIRE(d.D <= 8, EAV_ERR_UNSUPPORTED, "dw_bwd: D=%d > 8 unsupported", d.D);
+    const int TS = d.T + 1;
+    size_t fl = (size_t)((d.C * TS + 3) & ~3) + (size_t)d.T * 8 + 8 * d.C + (size_t)DB_TS * d.D * d.C;
+    size_t smem = fl * sizeof(float);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "dw_bwd: Chans*Samples too large for one CTA");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dw_bwd_kernel<<<d.N * d.F1, DB_THREADS, smem, st>>>(dz2, y2, bnf2, bnb2, y1, bnf1, params, d.pstride, d.oW2,
+                                                       d.bn_train, d.variant == EAV_VARIANT_TOR, d.B, d.F1, d.D,
+                                                       d.C, d.T, dz1, part_w, part_bn);
+    EAV_CUDA_LAUNCH_CHECK("dw_bwd");
+    // part_w is [N][G*C]: reduce over the B samples of each model
+    return launch_reduce_partials(part_w, d.B, (int64_t)d.G * d.C, d.M, d.pstride, grads + d.oW2, st);
+}
+
+// =================================================================================
+// M1 weight gradient:  dW1[m,f,k] = sum_{b,c,t} dy1[n,f,c,t] * x[n,c,t+k-pad1l]
+// (72.0 MFLOP per epoch; the reference spends 54 % of its step here).
+// One warp per (n,c) row: lane owns RK consecutive lags k for all F1 filters
+// (F1*RK accumulators) and walks t four at a time: 8 broadcast LDS.128 (dy1 as [t][f]) +
+// RK/2+2 LDS.64 (x window) per 4*F1*RK FFMA.  A CTA (4 warps) walks a contiguous range
+// of rows of ONE model and writes one partial; reduce_partials sums them in order.
+// =================================================================================
+constexpr int TW_WARPS = 4;
+constexpr int TW_TCH = 128;     // time steps of dy1 staged per pass
+
+template <int F1, int RK>
+__global__ void __launch_bounds__(TW_WARPS * 32, 3)
+tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
+                    const float *__restrict__ dz1, const float *__restrict__ y1,
+                    const float4 *__restrict__ bnf1, const float4 *__restrict__ bnb1, int bn_train, int B,
+                    int C, int T, int K1, int padl, int ctas_per_model, float *__restrict__ part) {
+    extern __shared__ __align__(16) float smem[];
+    const int Tp = (T + 3) & ~3;
+    const int XS = (Tp + 32 * RK + 8 + 3) & ~3;      // x row incl. both paddings
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *xs = smem + warp * (XS + TW_TCH * F1);    // per-warp private staging
+    float *dys = xs + XS;                            // [TW_TCH][F1]
+    const int m = blockIdx.x / ctas_per_model, j = blockIdx.x - m * ctas_per_model;
+    const int rows = B * C;                          // rows of this model
+    const int r_lo = (int)((int64_t)rows * j / ctas_per_model), r_hi = (int)((int64_t)rows * (j + 1) / ctas_per_model);
+
+    float acc[F1][RK];
+#pragma unroll
+    for (int f = 0; f < F1; ++f)
+#pragma unroll
+        for (int q = 0; q < RK; ++q) acc[f][q] = 0.f;
+
+    for (int r = r_lo + warp; r < r_hi; r += TW_WARPS) {
+        const int b = r / C, c = r - b * C;
+        const int64_t n = (int64_t)m * B + b;
+        const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
+        __syncwarp();
+        // xs[i] = x[i - padl], zero padded
+        const float *xsrc = x + (xrow * C + c) * (int64_t)T;
+        for (int i = lane; i < XS; i += 32) {
+            int t = i - padl;
+            xs[i] = (t >= 0 && t < T) ? xsrc[t] : 0.f;
+        }
+        for (int tc = 0; tc < Tp; tc += TW_TCH) {
+            const int tn = min(TW_TCH, Tp - tc);     // multiple of 4
+            __syncwarp();
+#pragma unroll
+            for (int f = 0; f < F1; ++f) {
+                const float4 kb = bnb1[(int64_t)m * F1 + f];
+                const float4 kf = bnf1[(int64_t)m * F1 + f];
+                const int64_t base = ((n * F1 + f) * C + c) * (int64_t)T + tc;
+                for (int t = lane; t < tn; t += 32) {
+                    float v = 0.f;
+                    if (tc + t < T) {
+                        v = dz1[base + t];
+                        if (bn_train) v = kb.x * (v - kb.y - (y1[base + t] - kf.x) * kf.y * kb.z);
+                        else v = kb.x * v;
+                    }
+                    dys[t * F1 + f] = v;
+                }
+            }
+            __syncwarp();
+            const float *xr = xs + lane * RK + tc;
+#pragma unroll 1
+            for (int t = 0; t < tn; t += 4) {
+                float xw[RK + 4];
+#pragma unroll
+                for (int q = 0; q < (RK + 4) / 2; ++q) {
+                    float2 v = *reinterpret_cast<const float2 *>(xr + t + 2 * q);
+                    xw[2 * q] = v.x; xw[2 * q + 1] = v.y;
+                }
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) {
+                    float dv[F1];
+#pragma unroll
+                    for (int q = 0; q < F1 / 4; ++q) {
+                        float4 v = *reinterpret_cast<const float4 *>(dys + (t + tt) * F1 + 4 * q);
+                        dv[4 * q] = v.x; dv[4 * q + 1] = v.y; dv[4 * q + 2] = v.z; dv[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int f = 0; f < F1; ++f)
+#pragma unroll
+                        for (int q = 0; q < RK; ++q) acc[f][q] = fmaf(dv[f], xw[tt + q], acc[f][q]);
+                }
+            }
+        }
+    }
+    // cross-warp reduction through smem (reuse the staging area), then one partial per CTA
+    __syncthreads();
+    float *red = smem;   // [TW_WARPS][F1][32*RK]
+#pragma unroll
+    for (int f = 0; f < F1; ++f)
+#pragma unroll
+        for (int q = 0; q < RK; ++q) red[(warp * F1 + f) * (32 * RK) + lane * RK + q] = acc[f][q];
+    __syncthreads();
+    for (int i = threadIdx.x; i < F1 * K1; i += blockDim.x) {
+        int f = i / K1, k = i - f * K1;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < TW_WARPS; ++w) s += red[(w * F1 + f) * (32 * RK) + k];
+        part[((int64_t)m * ctas_per_model + j) * (F1 * K1) + i] = s;
+    }
+}
+
+template <int RK>
+static size_t tconv_dw_smem(int T) {
+    const int Tp = (T + 3) & ~3;
+    const int XS = (Tp + 32 * RK + 8 + 3) & ~3;
+    size_t stage = (size_t)TW_WARPS * (XS + TW_TCH * 8) * sizeof(float);
+    size_t redb = (size_t)TW_WARPS * 8 * 32 * RK * sizeof(float);
+    return stage > redb ? stage : redb;
+}
+
+static int tconv_rk(int K1) { return K1 <= 64 ? 2 : K1 <= 128 ? 4 : K1 <= 256 ? 8 : K1 <= 320 ? 10 : 16; }
+
+int tconv_dw_ctas_per_model(const NetDims &d) {
+    // ~two full waves of resident CTAs (148 SMs x up to 3 CTAs) when the work allows it
+    int64_t rows = (int64_t)d.B * d.C;
+    int64_t want = (148 * 3 * 2) / d.M;
+    int64_t cap = cdiv64(rows, TW_WARPS);   // at least one row per warp
+    int64_t c = want < cap ? want : cap;
+    if (c < 1) c = 1;
+    return (int)c;
+}
+
+template <int RK>
+static int launch_tconv_bwd_dw_rk(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
+                                  const float *y1, const float4 *bnf1, const float4 *bnb1, float *part,
+                                  cudaStream_t st, int cpm) {
+    size_t smem = tconv_dw_smem<RK>(d.T);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: Samples=%d too large", d.T);
+    cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    tconv_bwd_dw_kernel<8, RK><<<d.M * cpm, TW_WARPS * 32, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train,
+                                                                       d.B, d.C, d.T, d.K1, d.pad1l, cpm, part);
+    return 0;
+}
+
+int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
+                        const float *y1, const float4 *bnf1, const float4 *bnb1, float *part, float *grads,
+                        cudaStream_t st) {
+    EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: F1=%d unsupported (only 8)", d.F1);
+    EAV_REQUIRE(d.K1 <= 512, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: kernLength=%d > 512 unsupported", d.K1);
+    const int cpm = tconv_dw_ctas_per_model(d);
+    int rc;
+    switch (tconv_rk(d.K1)) {
+        case 2: rc = launch_tconv_bwd_dw_rk<2>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;
+        case 4: rc = launch_tconv_bwd_dw_rk<4>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;
+        case 8: rc = launch_tconv_bwd_dw_rk<8>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;
+        case 10: rc = launch_tconv_bwd_dw_rk<10>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;
+        default: rc = launch_tconv_bwd_dw_rk<16>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;
+    }
+    if (rc) return rc;
+    EAV_CUDA_LAUNCH_CHECK("tconv_bwd_dw");
+    return launch_reduce_partials(part, cpm, (int64_t)d.F1 * d.K1, d.M, d.pstride, grads + d.oW1, st);
+}
+
+}  // namespace eav

@@ -1,0 +1,638 @@
+// Forward kernels of the EEGNet path (CNN_torch/EEGNet_tor.py:50-67, CNN_torch/CNN_EEG.py:57-67)
+// for sm_100a.  Data layout: activations [N][channels][time] fp32, N = M*B samples of M
+// independent models (sample n belongs to model n / B); parameters are read from the
+// flat per-model arena (NetDims offsets).
+#include "eegnet_kernels.cuh"
+
+namespace eav {
+
+// =================================================================================
+// M1  temporal convolution, register-blocked sliding window on the CUDA cores.
+//   y1[n,f,c,t] = sum_k W1[f,k] * x[n,c,t+k-pad1l]          (EEGNet_tor.py:24,51)
+// CTA = 4 channel rows x 512 time outputs; 64 threads per row, each thread keeps
+// F1 x 8 accumulators and walks the taps 4 at a time: per 4 taps it issues 3 LDS.128 for
+// the x window, 8 broadcast LDS.128 for the weights and 256 FFMA (95.9 % FFMA issue).
+// Algorithmic work: 2*K1*F1 flop per output sample -> 72.0 MFLOP per EEG epoch.
+// =================================================================================
+constexpr int TC_ROWS = 4;      // channel rows per CTA
+constexpr int TC_R = 8;         // outputs per thread
+constexpr int TC_TPR = 64;      // threads per row
+constexpr int TC_TT = TC_R * TC_TPR;  // 512 time outputs per CTA tile
+
+template <int F1>
+__global__ void __launch_bounds__(TC_ROWS *TC_TPR, 2)
+tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
+                 const float *__restrict__ params, int64_t pstride, int64_t oW1, int B, int C,
+                 int T, int K1, int padl, float *__restrict__ y1, float *__restrict__ part) {
+    extern __shared__ __align__(16) float smem[];
+    const int K1p = (K1 + 3) & ~3;
+    const int XS = TC_TT + K1p + 4;  // multiple of 4
+    float *ws = smem;                // [K1p][F1]
+    float *xs = smem + K1p * F1;     // [TC_ROWS][XS]
+
+    const int n = blockIdx.z, m = n / B;
+    const int c0 = blockIdx.y * TC_ROWS;
+    const int tile0 = blockIdx.x * TC_TT;
+    const int tid = threadIdx.x;
+    const int64_t xrow = x_index ? (int64_t)x_index[n] : (int64_t)n;
+
+    const float *W1 = params + (int64_t)m * pstride + oW1;
+    for (int i = tid; i < K1p * F1; i += blockDim.x) {
+        int k = i / F1, f = i - k * F1;
+        ws[i] = (k < K1) ? W1[f * K1 + k] : 0.f;
+    }
+    for (int i = tid; i < TC_ROWS * XS; i += blockDim.x) {
+        int r = i / XS, j = i - r * XS;
+        int c = c0 + r, t = tile0 - padl + j;
+        float v = 0.f;
+        if (c < C && t >= 0 && t < T) v = x[(xrow * C + c) * (int64_t)T + t];
+        xs[i] = v;
+    }
+    __syncthreads();
+
+    const int r = tid / TC_TPR, j = tid - r * TC_TPR;
+    const int t0 = j * TC_R;
+    const float *xr = xs + r * XS + t0;
+    float acc[F1][TC_R];
+#pragma unroll
+    for (int f = 0; f < F1; ++f)
+#pragma unroll
+        for (int q = 0; q < TC_R; ++q) acc[f][q] = 0.f;
+
+    for (int k0 = 0; k0 < K1p; k0 += 4) {
+        float xw[TC_R + 4];
+#pragma unroll
+        for (int q = 0; q < (TC_R + 4) / 4; ++q) {
+            float4 v = *reinterpret_cast<const float4 *>(xr + k0 + 4 * q);
+            xw[4 * q + 0] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            float w[F1];
+#pragma unroll
+            for (int q = 0; q < F1 / 4; ++q) {
+                float4 v = *reinterpret_cast<const float4 *>(ws + (k0 + kk) * F1 + 4 * q);
+                w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int f = 0; f < F1; ++f)
+#pragma unroll
+                for (int q = 0; q < TC_R; ++q) acc[f][q] = fmaf(w[f], xw[kk + q], acc[f][q]);
+        }
+    }
+
+    const int c = c0 + r;
+    const int tg = tile0 + t0;
+    const bool row_ok = c < C;
+    if (row_ok) {
+#pragma unroll
+        for (int f = 0; f < F1; ++f) {
+            float *dst = y1 + (((int64_t)n * F1 + f) * C + c) * (int64_t)T + tg;
+            if ((T & 3) == 0 && tg + TC_R <= T) {
+                reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
+                reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < TC_R; ++q)
+                    if (tg + q < T) dst[q] = acc[f][q];
+            }
+        }
+    }
+    if (part != nullptr) {
+        // per-CTA partial sums for BatchNorm statistics (deterministic two-stage reduction)
+        __shared__ float red[(TC_ROWS * TC_TPR / 32)][2 * F1];
+        const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+        for (int f = 0; f < F1; ++f) {
+            float s = 0.f, q2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < TC_R; ++q) {
+                float v = (row_ok && tg + q < T) ? acc[f][q] : 0.f;
+                s += v;
+                q2 = fmaf(v, v, q2);
+            }
+            s = warp_sum(s);
+            q2 = warp_sum(q2);
+            if (lane == 0) { red[warp][2 * f] = s; red[warp][2 * f + 1] = q2; }
+        }
+        __syncthreads();
+        if (tid < 2 * F1) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < TC_ROWS * TC_TPR / 32; ++w) s += red[w][tid];
+            int64_t row = ((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            part[row * (2 * F1) + tid] = s;
+        }
+    }
+}
+
+int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
+                     float *y1, float *part, int *part_rows, cudaStream_t st) {
+    EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_fwd: F1=%d unsupported (only 8)", d.F1);
+    const int K1p = (d.K1 + 3) & ~3;
+    const int XS = TC_TT + K1p + 4;
+    size_t smem = (size_t)(K1p * d.F1 + TC_ROWS * XS) * sizeof(float);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_fwd: kernLength %d too large", d.K1);
+    dim3 grid(cdiv(d.T, TC_TT), cdiv(d.C, TC_ROWS), d.N);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tconv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    tconv_fwd_kernel<8><<<grid, TC_ROWS * TC_TPR, smem, st>>>(x, x_index, params, d.pstride, d.oW1, d.B,
+                                                            d.C, d.T, d.K1, d.pad1l, y1, part);
+    EAV_CUDA_LAUNCH_CHECK("tconv_fwd");
+    if (part_rows) *part_rows = d.B * grid.y * grid.x;
+    return 0;
+}
+
+// =================================================================================
+// BatchNorm statistics (nn.BatchNorm2d, eps/momentum as the reference: EEGNet_tor.py:25,29,38)
+// part: [M][rows_per_model][ch][2] fp32 partial (sum, sum of squares); one warp per
+// (channel, model) reduces them in fp64 in a fixed order.
+// =================================================================================
+__global__ void bn_finalize_kernel(const float *__restrict__ part, int rows_per_model, int ch,
+                                   double count, const float *__restrict__ params, int64_t pstride,
+                                   int64_t og, int64_t ob, float *__restrict__ bn_state,
+                                   int64_t bnstride, int64_t orm, int64_t orv, int bn_train,
+                                   float eps, float momentum, float4 *__restrict__ stats) {
+    const int c = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+    float *rm = bn_state + (int64_t)m * bnstride + orm;
+    float *rv = bn_state + (int64_t)m * bnstride + orv;
+    float mean, var;
+    if (bn_train) {
+        double s = 0.0, q = 0.0;
+        const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
+        for (int r = lane; r < rows_per_model; r += 32) {
+            s += (double)p[((int64_t)r * ch + c) * 2];
+            q += (double)p[((int64_t)r * ch + c) * 2 + 1];
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        double mu = s / count;
+        double vb = q / count - mu * mu;
+        if (vb < 0.0) vb = 0.0;
+        mean = (float)mu;
+        var = (float)vb;
+        if (lane == 0) {
+            double unbiased = count > 1.0 ? vb * count / (count - 1.0) : vb;
+            rm[c] = (1.f - momentum) * rm[c] + momentum * mean;
+            rv[c] = (1.f - momentum) * rv[c] + momentum * (float)unbiased;
+        }
+    } else {
+        mean = rm[c];
+        var = rv[c];
+    }
+    if (lane == 0) {
+        float invstd = 1.0f / sqrtf(var + eps);
+        float g = params[(int64_t)m * pstride + og + c];
+        float b = params[(int64_t)m * pstride + ob + c];
+        float scale = g * invstd;
+        stats[(int64_t)m * ch + c] = make_float4(mean, invstd, scale, b - mean * scale);
+    }
+}
+
+int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
+                       double count, const float *params, float *bn_state, float4 *stats,
+                       cudaStream_t st) {
+    int ch;
+    int64_t og, ob, orm, orv;
+    if (layer == 1) { ch = d.F1; og = d.og1; ob = d.ob1; orm = d.orm1; orv = d.orv1; }
+    else if (layer == 2) { ch = d.G; og = d.og2; ob = d.ob2; orm = d.orm2; orv = d.orv2; }
+    else { ch = d.F2; og = d.og3; ob = d.ob3; orm = d.orm3; orv = d.orv3; }
+    bn_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, params, d.pstride,
+                                                     og, ob, bn_state, d.bnstride, orm, orv, d.bn_train,
+                                                     d.eps, d.momentum, stats);
+    EAV_CUDA_LAUNCH_CHECK("bn_finalize");
+    return 0;
+}
+
+// =================================================================================
+// M2+M3+M4  BN1 (+ELU for variant 0) + depthwise spatial conv over the electrodes.
+//   y2[n, f*D+d, t] = sum_c W2[f*D+d, c] * act(y1[n,f,c,t]*scale1[f] + shift1[f])
+// HBM/L2-bound: reads y1 once (F1*C*T floats per sample), writes G*T.
+// =================================================================================
+constexpr int DW_THREADS = 128;
+constexpr int DMAX = 8;
+
+__global__ void __launch_bounds__(DW_THREADS)
+dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, int64_t pstride,
+              int64_t oW2, const float4 *__restrict__ bn1, int B, int F1, int D, int C, int T,
+              int elu1, float *__restrict__ y2, float *__restrict__ part) {
+    extern __shared__ float w2s[];  // [D][C]
+    __shared__ float red[DW_THREADS / 32][2 * DMAX];
+    const int n = blockIdx.z, f = blockIdx.y, m = n / B;
+    const int t = blockIdx.x * DW_THREADS + threadIdx.x;
+    const int G = F1 * D;
+    const float *W2 = params + (int64_t)m * pstride + oW2 + (int64_t)f * D * C;
+    for (int i = threadIdx.x; i < D * C; i += DW_THREADS) w2s[i] = W2[i];
+    const float4 st = bn1[(int64_t)m * F1 + f];
+    __syncthreads();
+    float acc[DMAX];
+#pragma unroll
+    for (int dd = 0; dd < DMAX; ++dd) acc[dd] = 0.f;
+    if (t < T) {
+        const float *src = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T + t;
+        for (int c = 0; c < C; ++c) {
+            float v = fmaf(src[(int64_t)c * T], st.z, st.w);
+            float a = elu1 ? elu_f(v) : v;
+#pragma unroll
+            for (int dd = 0; dd < DMAX; ++dd)
+                if (dd < D) acc[dd] = fmaf(w2s[dd * C + c], a, acc[dd]);
+        }
+#pragma unroll
+        for (int dd = 0; dd < DMAX; ++dd)
+            if (dd < D) y2[((int64_t)n * G + f * D + dd) * (int64_t)T + t] = acc[dd];
+    }
+    if (part != nullptr) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int dd = 0; dd < DMAX; ++dd) {
+            float v = (t < T && dd < D) ? acc[dd] : 0.f;
+            float s = warp_sum(v), q = warp_sum(v * v);
+            if (lane == 0) { red[warp][2 * dd] = s; red[warp][2 * dd + 1] = q; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 * D) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < DW_THREADS / 32; ++w) s += red[w][threadIdx.x];
+            int64_t row = (int64_t)n * gridDim.x + blockIdx.x;
+            int dd = threadIdx.x >> 1, which = threadIdx.x & 1;
+            part[(row * G + f * D + dd) * 2 + which] = s;
+        }
+    }
+}
+
+int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
+                  float *y2, float *part, int *part_rows, cudaStream_t st) {
+    EAV_REQUIRE(d.D <= DMAX, EAV_ERR_UNSUPPORTED, "dw_fwd: D=%d > %d unsupported", d.D, DMAX);
+    dim3 grid(cdiv(d.T, DW_THREADS), d.F1, d.N);
+    dw_fwd_kernel<<<grid, DW_THREADS, (size_t)d.D * d.C * sizeof(float), st>>>(
+        y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, d.variant == EAV_VARIANT_TOR, y2, part);
+    EAV_CUDA_LAUNCH_CHECK("dw_fwd");
+    if (part_rows) *part_rows = d.B * grid.x;
+    return 0;
+}
+
+// =================================================================================
+// M5  BN2 + ELU + AvgPool2d((1,P1)) + dropout -> d1[n,g,u]
+// =================================================================================
+__global__ void pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
+                                 const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1,
+                                 int dropout_mode, float p_drop, uint64_t seed, uint64_t step,
+                                 int64_t total, float *__restrict__ d1) {
+    const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int u = (int)(i % T4);
+        int64_t ng = i / T4;
+        int g = (int)(ng % G);
+        int n = (int)(ng / G);
+        const float4 st = bn2[(int64_t)(n / B) * G + g];
+        const float *src = y2 + ng * (int64_t)T + (int64_t)u * P1;
+        float s = 0.f;
+        for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+        s *= 1.f / (float)P1;
+        if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[i] ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 1u, (uint64_t)i, p_drop) ? s * inv_keep : 0.f;
+        d1[i] = s;
+    }
+}
+
+int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const uint8_t *mask1,
+                     float *d1, cudaStream_t st) {
+    int64_t total = (int64_t)d.N * d.G * d.T4;
+    int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
+    pool1_fwd_kernel<<<blocks, 256, 0, st>>>(y2, bn2, mask1, d.B, d.G, d.T, d.T4, d.P1, d.dropout_mode,
+                                             d.p_drop, d.seed, d.step, total, d1);
+    EAV_CUDA_LAUNCH_CHECK("pool1_fwd");
+    return 0;
+}
+
+// =================================================================================
+// M6  (1,16) 'same' convolution over all input channels (EEGNet_tor.py:37,59) and its
+// input gradient (MODE 1), as a register-blocked implicit GEMM on the CUDA cores:
+//   MODE 0: out[n,o,u] = sum_g sum_k W3[o,g,k] * in[n,g,u+k-7]          in = d1
+//   MODE 1: out[n,g,u] = sum_o sum_k W3[o,g,15-k] * in[n,o,u+k-8]       in = dy3 (BN3 bwd applied on load)
+// CTA = 2 samples of one model x 64 output channels x 128 positions; thread = 8 channels x
+// 4 positions x 2 samples (64 accumulators); weights streamed through smem 4 input
+// channels at a time.  16.4 MFLOP per epoch per direction.
+// =================================================================================
+constexpr int SC_K = 16;       // kernel length (fixed by the reference)
+constexpr int SC_SC = 2;       // samples per CTA
+constexpr int SC_GC = 4;       // input channels per weight chunk
+constexpr int SC_UT = 128;     // positions per CTA
+constexpr int SC_XS = SC_UT + SC_K;  // 144: padded input row
+constexpr int SC_CO = 64;      // output channels per CTA
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
+               const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
+               const float *__restrict__ params, int64_t pstride, int64_t oW3, int B, int Cin, int Cout,
+               int L, int padl, float *__restrict__ out, float *__restrict__ part) {
+    extern __shared__ __align__(16) float smem[];
+    float *ws = smem;                            // [SC_GC][SC_CO][SC_K]
+    float *xs = smem + SC_GC * SC_CO * SC_K;     // [SC_SC][Cin][SC_XS]
+    const int pairs = (B + SC_SC - 1) / SC_SC;
+    const int m = blockIdx.z / pairs, pair = blockIdx.z - m * pairs;
+    const int o_base = blockIdx.y * SC_CO;
+    const int u0 = blockIdx.x * SC_UT;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const float *W3 = params + (int64_t)m * pstride + oW3;
+
+    // stage the input rows (with the BatchNorm-backward transform in MODE 1)
+    for (int i = tid; i < SC_SC * Cin * SC_XS; i += 256) {
+        int s = i / (Cin * SC_XS);
+        int rem = i - s * Cin * SC_XS;
+        int ch = rem / SC_XS, j = rem - ch * SC_XS;
+        int b = pair * SC_SC + s;
+        int u = u0 - padl + j;
+        float v = 0.f;
+        if (b < B && u >= 0 && u < L) {
+            int64_t idx = (((int64_t)(m * B + b)) * Cin + ch) * (int64_t)L + u;
+            v = in[idx];
+            if (MODE == 1) {
+                const float4 kb = bnb[(int64_t)m * Cin + ch];
+                if (bn_train) {
+                    const float4 kf = bnf[(int64_t)m * Cin + ch];
+                    float xhat = (yraw[idx] - kf.x) * kf.y;
+                    v = kb.x * (v - kb.y - xhat * kb.z);
+                } else {
+                    v = kb.x * v;
+                }
+            }
+        }
+        xs[i] = v;
+    }
+
+    float acc[SC_SC][8][4];
+#pragma unroll
+    for (int s = 0; s < SC_SC; ++s)
+#pragma unroll
+        for (int oo = 0; oo < 8; ++oo)
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) acc[s][oo][uu] = 0.f;
+
+    for (int g0 = 0; g0 < Cin; g0 += SC_GC) {
+        __syncthreads();
+        for (int i = tid; i < SC_GC * SC_CO * SC_K; i += 256) {
+            int gl = i / (SC_CO * SC_K);
+            int rem = i - gl * SC_CO * SC_K;
+            int o = rem / SC_K, k = rem - o * SC_K;
+            float w = 0.f;
+            int gi = g0 + gl, oc = o_base + o;
+            if (gi < Cin && oc < Cout) {
+                if (MODE == 0) w = W3[((int64_t)oc * Cin + gi) * SC_K + k];            // W3[o][g][k]
+                else           w = W3[((int64_t)gi * Cout + oc) * SC_K + (SC_K - 1 - k)]; // W3[o'=gi][g=oc][15-k]
+            }
+            ws[i] = w;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int gl = 0; gl < SC_GC; ++gl) {
+            if (g0 + gl >= Cin) break;
+            float xw[SC_SC][20];
+#pragma unroll
+            for (int s = 0; s < SC_SC; ++s) {
+                const float *xr = xs + ((int64_t)s * Cin + g0 + gl) * SC_XS + 4 * threadIdx.x;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    float4 v = *reinterpret_cast<const float4 *>(xr + 4 * q);
+                    xw[s][4 * q] = v.x; xw[s][4 * q + 1] = v.y; xw[s][4 * q + 2] = v.z; xw[s][4 * q + 3] = v.w;
+                }
+            }
+            const float *wr = ws + (gl * SC_CO + 8 * threadIdx.y) * SC_K;
+#pragma unroll
+            for (int k = 0; k < SC_K; k += 4) {
+#pragma unroll
+                for (int oo = 0; oo < 8; ++oo) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(wr + oo * SC_K + k);
+                    const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                        for (int s = 0; s < SC_SC; ++s)
+#pragma unroll
+                            for (int uu = 0; uu < 4; ++uu)
+                                acc[s][oo][uu] = fmaf(wv[kk], xw[s][k + kk + uu], acc[s][oo][uu]);
+                }
+            }
+        }
+    }
+
+    const int ub = u0 + 4 * threadIdx.x;
+#pragma unroll
+    for (int oo = 0; oo < 8; ++oo) {
+        const int oc = o_base + 8 * threadIdx.y + oo;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int s = 0; s < SC_SC; ++s) {
+            const int b = pair * SC_SC + s;
+            if (b < B && oc < Cout) {
+                float *dst = out + (((int64_t)(m * B + b)) * Cout + oc) * (int64_t)L + ub;
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu)
+                    if (ub + uu < L) {
+                        dst[uu] = acc[s][oo][uu];
+                        s1 += acc[s][oo][uu];
+                        s2 = fmaf(acc[s][oo][uu], acc[s][oo][uu], s2);
+                    }
+            }
+        }
+        if (MODE == 0 && part != nullptr) {
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (threadIdx.x == 0 && oc < Cout) {
+                int64_t row = ((int64_t)m * pairs + pair) * gridDim.x + blockIdx.x;
+                part[(row * Cout + oc) * 2] = s1;
+                part[(row * Cout + oc) * 2 + 1] = s2;
+            }
+        }
+    }
+}
+
+static size_t sepconv_smem(int Cin) {
+    return (size_t)(SC_GC * SC_CO * SC_K + SC_SC * Cin * SC_XS) * sizeof(float);
+}
+
+int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *y3,
+                       float *part, int *part_rows, cudaStream_t st) {
+    EAV_REQUIRE(d.K2 == SC_K, EAV_ERR_UNSUPPORTED, "sepconv: kernel length %d unsupported (only 16)", d.K2);
+    size_t smem = sepconv_smem(d.G);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv: F1*D=%d too large", d.G);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sepconv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int pairs = cdiv(d.B, SC_SC);
+    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.F2, SC_CO), d.M * pairs);
+    sepconv_kernel<0><<<grid, dim3(32, 8), smem, st>>>(d1, nullptr, nullptr, nullptr, 0, params, d.pstride,
+                                                       d.oW3, d.B, d.G, d.F2, d.T4, d.pad2l, y3, part);
+    EAV_CUDA_LAUNCH_CHECK("sepconv_fwd");
+    if (part_rows) *part_rows = pairs * grid.x;
+    return 0;
+}
+
+int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                          const float4 *bnb3, const float *params, float *dd1, cudaStream_t st) {
+    size_t smem = sepconv_smem(d.F2);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv_dx: F2=%d too large", d.F2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sepconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int pairs = cdiv(d.B, SC_SC);
+    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.G, SC_CO), d.M * pairs);
+    // flipped kernel: left padding K-1-pad2l
+    sepconv_kernel<1><<<grid, dim3(32, 8), smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, params, d.pstride,
+                                                       d.oW3, d.B, d.F2, d.G, d.T4, d.K2 - 1 - d.pad2l, dd1,
+                                                       nullptr);
+    EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dx");
+    return 0;
+}
+
+// =================================================================================
+// Variant 1 (CNN_EEG.py:35-37) block 2: depthwise temporal conv, then pointwise conv.
+// =================================================================================
+__global__ void dwt_fwd_kernel(const float *__restrict__ d1, const float *__restrict__ params,
+                               int64_t pstride, int64_t oW3, int B, int G, int L, int K2, int padl,
+                               int64_t total, float *__restrict__ y3d) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int u = (int)(i % L);
+        int64_t ng = i / L;
+        int g = (int)(ng % G), n = (int)(ng / G);
+        const float *w = params + (int64_t)(n / B) * pstride + oW3 + (int64_t)g * K2;
+        const float *src = d1 + ng * (int64_t)L;
+        float s = 0.f;
+        for (int k = 0; k < K2; ++k) {
+            int uu = u + k - padl;
+            if (uu >= 0 && uu < L) s = fmaf(w[k], src[uu], s);
+        }
+        y3d[i] = s;
+    }
+}
+
+int launch_dwt_fwd(const NetDims &d, const float *d1, const float *params, float *y3d, cudaStream_t st) {
+    int64_t total = (int64_t)d.N * d.G * d.T4;
+    int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
+    dwt_fwd_kernel<<<blocks, 256, 0, st>>>(d1, params, d.pstride, d.oW3, d.B, d.G, d.T4, d.K2, d.pad2l, total, y3d);
+    EAV_CUDA_LAUNCH_CHECK("dwt_fwd");
+    return 0;
+}
+
+// pointwise: y3[n,o,u] = sum_g W3p[o,g] * y3d[n,g,u]; one warp-row per (n,o): lanes over u.
+__global__ void __launch_bounds__(128)
+pw_fwd_kernel(const float *__restrict__ y3d, const float *__restrict__ params, int64_t pstride,
+              int64_t oW3p, int B, int G, int F2, int L, float *__restrict__ y3, float *__restrict__ part) {
+    extern __shared__ float wsh[];  // [G]
+    const int n = blockIdx.y, o = blockIdx.x, m = n / B;
+    const float *w = params + (int64_t)m * pstride + oW3p + (int64_t)o * G;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) wsh[i] = w[i];
+    __syncthreads();
+    float s1 = 0.f, s2 = 0.f;
+    for (int u = threadIdx.x; u < L; u += blockDim.x) {
+        const float *src = y3d + ((int64_t)n * G) * L + u;
+        float s = 0.f;
+        for (int g = 0; g < G; ++g) s = fmaf(wsh[g], src[(int64_t)g * L], s);
+        y3[((int64_t)n * F2 + o) * L + u] = s;
+        s1 += s;
+        s2 = fmaf(s, s, s2);
+    }
+    if (part != nullptr) {
+        __shared__ float red[4][2];
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = s1; red[threadIdx.x >> 5][1] = s2; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            float s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+            part[((int64_t)n * F2 + o) * 2 + threadIdx.x] = s;   // one partial row per sample
+        }
+    }
+}
+
+int launch_pw_fwd(const NetDims &d, const float *y3d, const float *params, float *y3, float *part,
+                  int *part_rows, cudaStream_t st) {
+    pw_fwd_kernel<<<dim3(d.F2, d.N), 128, (size_t)d.G * sizeof(float), st>>>(y3d, params, d.pstride, d.oW3p,
+                                                                           d.B, d.G, d.F2, d.T4, y3, part);
+    EAV_CUDA_LAUNCH_CHECK("pw_fwd");
+    if (part_rows) *part_rows = d.B;
+    return 0;
+}
+
+// =================================================================================
+// M7+M8  BN3 + ELU + AvgPool2d((1,P2)) + dropout + flatten + dense (+ softmax).
+// One CTA per sample.  The max-norm hook on the dense weight runs AFTER this kernel
+// (separate launch) so that the forward uses W_old.
+// =================================================================================
+__global__ void __launch_bounds__(128)
+tail_fwd_kernel(const float *__restrict__ y3, const float4 *__restrict__ bn3,
+                const uint8_t *__restrict__ mask2, const float *__restrict__ params, int64_t pstride,
+                int64_t oWd, int64_t obd, int B, int F2, int T4, int T32, int P2, int NC, int softmax_out,
+                int dropout_mode, float p_drop, uint64_t seed, uint64_t step,
+                float *__restrict__ feat, float *__restrict__ out, float *__restrict__ probs_saved) {
+    extern __shared__ float sm[];  // feat_s[FEAT] + z_s[NC]
+    const int FEAT = F2 * T32;
+    float *feat_s = sm, *z_s = sm + FEAT;
+    const int n = blockIdx.x, m = n / B, tid = threadIdx.x;
+    const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
+    for (int i = tid; i < FEAT; i += blockDim.x) {
+        int o = i / T32, v = i - o * T32;
+        const float4 st = bn3[(int64_t)m * F2 + o];
+        const float *src = y3 + ((int64_t)n * F2 + o) * T4 + v * P2;
+        float s = 0.f;
+        for (int w = 0; w < P2; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+        s *= 1.f / (float)P2;
+        int64_t e = (int64_t)n * FEAT + i;
+        if (dropout_mode == EAV_DROPOUT_MASK) s = mask2[e] ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 2u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        feat_s[i] = s;
+        feat[e] = s;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    const float *Wd = params + (int64_t)m * pstride + oWd;
+    for (int j = warp; j < NC; j += blockDim.x >> 5) {
+        float s = 0.f;
+        for (int i = lane; i < FEAT; i += 32) s = fmaf(Wd[(int64_t)j * FEAT + i], feat_s[i], s);
+        s = warp_sum(s);
+        if (lane == 0) z_s[j] = s + params[(int64_t)m * pstride + obd + j];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (softmax_out) {
+            float mx = -INFINITY;
+            for (int j = 0; j < NC; ++j) mx = fmaxf(mx, z_s[j]);
+            float den = 0.f;
+            for (int j = 0; j < NC; ++j) den += expf(z_s[j] - mx);
+            for (int j = 0; j < NC; ++j) {
+                float p = expf(z_s[j] - mx) / den;
+                out[(int64_t)n * NC + j] = p;
+                probs_saved[(int64_t)n * NC + j] = p;
+            }
+        } else {
+            for (int j = 0; j < NC; ++j) {
+                out[(int64_t)n * NC + j] = z_s[j];
+                probs_saved[(int64_t)n * NC + j] = z_s[j];
+            }
+        }
+    }
+}
+
+int launch_tail_fwd(const NetDims &d, const float *y3, const float4 *bn3, const uint8_t *mask2,
+                    const float *params, float *feat, float *out, float *probs_saved, cudaStream_t st) {
+    size_t smem = (size_t)(d.FEAT + d.NC) * sizeof(float);
+    EAV_REQUIRE(smem <= 48 * 1024, EAV_ERR_UNSUPPORTED, "tail_fwd: feature size %d too large", d.FEAT);
+    tail_fwd_kernel<<<d.N, 128, smem, st>>>(y3, bn3, mask2, params, d.pstride, d.oWd, d.obd, d.B, d.F2, d.T4,
+                                            d.T32, d.P2, d.NC, d.variant == EAV_VARIANT_TOR, d.dropout_mode,
+                                            d.p_drop, d.seed, d.step, feat, out, probs_saved);
+    EAV_CUDA_LAUNCH_CHECK("tail_fwd");
+    return 0;
+}
+
+}  // namespace eav

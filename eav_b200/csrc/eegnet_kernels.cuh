@@ -1,0 +1,65 @@
+// Launch-side declarations of the EEGNet kernels (definitions in eegnet_fwd.cu /
+// eegnet_bwd.cu / optim.cu).  Every launcher only enqueues work on `st`.
+#pragma once
+#include "eav_common.cuh"
+
+namespace eav {
+
+// ---- forward -------------------------------------------------------------------
+// M1: temporal conv (EEGNet_tor.py:24,51): x -> y1 raw [N][F1][C][T] (+ BN1 partial sums)
+int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
+                     float *y1, float *part, int *part_rows, cudaStream_t st);
+// M2/M5/M7 statistics: partial sums -> {mean, invstd, scale, shift}; running-stat update
+int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
+                       double count, const float *params, float *bn_state, float4 *stats,
+                       cudaStream_t st);
+// M2+M3+M4: BN1 (+ELU) + depthwise spatial conv -> y2 raw [N][G][T] (+ BN2 partial sums)
+int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
+                  float *y2, float *part, int *part_rows, cudaStream_t st);
+// M5: BN2 + ELU + AvgPool(1,P1) + dropout -> d1 [N][G][T4]
+int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const uint8_t *mask1,
+                     float *d1, cudaStream_t st);
+// M6: (1,K2) 'same' conv over G channels (variant 0) -> y3 raw [N][F2][T4] (+ BN3 partials)
+int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *y3,
+                       float *part, int *part_rows, cudaStream_t st);
+// variant 1 block 2: depthwise temporal conv + pointwise conv (CNN_EEG.py:35-37)
+int launch_dwt_fwd(const NetDims &d, const float *d1, const float *params, float *y3d, cudaStream_t st);
+int launch_pw_fwd(const NetDims &d, const float *y3d, const float *params, float *y3, float *part,
+                  int *part_rows, cudaStream_t st);
+// M7+M8: BN3 + ELU + AvgPool(1,P2) + dropout + flatten + dense (+ softmax) -> feat, out
+int launch_tail_fwd(const NetDims &d, const float *y3, const float4 *bn3, const uint8_t *mask2,
+                    const float *params, float *feat, float *out, float *probs_saved, cudaStream_t st);
+
+// ---- backward ------------------------------------------------------------------
+int launch_tail_bwd(const NetDims &d, const float *dout, const float *probs, const float *params,
+                    const float *y3, const float4 *bn3, const uint8_t *mask2, float *dz,
+                    float *dz3, float *part, cudaStream_t st);
+int launch_dense_bwd_w(const NetDims &d, const float *feat, const float *dz, float *grads, cudaStream_t st);
+int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
+                           double count, const float *params, const float4 *bnf, float4 *bnb,
+                           float *grads, cudaStream_t st);
+int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                          const float4 *bnb3, const float *params, float *dd1, cudaStream_t st);
+int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                          const float4 *bnb3, const float *d1, float *part, float *grads, cudaStream_t st);
+int launch_pw_bwd(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
+                  const float4 *bnb3, const float *y3d, const float *params, float *dy3d,
+                  float *part, float *grads, cudaStream_t st);
+int launch_dwt_bwd(const NetDims &d, const float *dy3d, const float *d1, const float *params,
+                   float *dd1, float *part, float *grads, cudaStream_t st);
+int launch_pool1_bwd(const NetDims &d, const float *dd1, const float *y2, const float4 *bnf2,
+                     const uint8_t *mask1, float *dz2, float *part, cudaStream_t st);
+int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const float4 *bnf2,
+                  const float4 *bnb2, const float *y1, const float4 *bnf1, const float *params,
+                  float *dz1, float *part_w, float *part_bn, float *grads, cudaStream_t st);
+int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
+                        const float *y1, const float4 *bnf1, const float4 *bnb1, float *part,
+                        float *grads, cudaStream_t st);
+
+// ---- small ops -------------------------------------------------------------------
+int launch_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_stride,
+                       int64_t rows_per_group, int64_t group_stride, float maxnorm, cudaStream_t st);
+int launch_reduce_partials(const float *part, int n_part, int64_t len, int n_models,
+                           int64_t dst_stride, float *dst, cudaStream_t st);
+
+}  // namespace eav

@@ -1,0 +1,200 @@
+/*
+ * eav_b200.h -- C ABI of libeav_b200.so: the B200 (sm_100a) implementation of the
+ * EEG hot path of nubcico/EAV.
+ *
+ * The reference is pure Python and has NO plugin / operator / FFI layer
+ * (SURVEY.md section 8b): its boundary is the Python class surface
+ *     Dataload_eeg.DataLoadEEG            (Dataload_eeg.py:35-160)
+ *     EAV_datasplit.EAVDataSplit          (EAV_datasplit.py:7-58)
+ *     CNN_torch.EEGNet_tor.{EEGNet_tor,Trainer_uni}   (CNN_torch/EEGNet_tor.py:15-135)
+ *     CNN_torch.CNN_EEG.{EEGNet,EEGNetTrainer}        (CNN_torch/CNN_EEG.py:7-162)
+ * which eav_b200/ mirrors in Python.  This header is the native layer those
+ * mirrors bind with ctypes; each entry point names the reference code it replaces.
+ *
+ * Conventions (all functions):
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every pointer argument marked "device" is a CUDA device pointer owned by the
+ *     caller; the library never allocates, frees or synchronises.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls only enqueue work, so they are CUDA-graph capturable.
+ *   - scratch memory comes from the caller: size it with *_workspace_bytes().
+ *   - return 0 on success, a negative EAV_ERR_* for argument errors, or a positive
+ *     cudaError_t from the launch; eav_last_error_string() describes the last
+ *     failure on the calling thread.
+ */
+#ifndef EAV_B200_H_
+#define EAV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAV_ABI_VERSION 1
+
+#define EAV_ERR_BAD_ARG      (-1)
+#define EAV_ERR_UNSUPPORTED  (-2)
+#define EAV_ERR_WORKSPACE    (-3)
+
+const char *eav_last_error_string(void);
+int eav_abi_version(void);
+/* 0 when the current device is compute capability 10.x, else EAV_ERR_UNSUPPORTED. */
+int eav_check_device(void);
+
+/* ------------------------------------------------------------------------- */
+/* Preprocessing: Dataload_eeg.py:85-152 (downsampling -> bandpass_filter ->
+ * segment_and_select_classes) for a batch of subjects.                       */
+/* ------------------------------------------------------------------------- */
+typedef struct eav_preproc_cfg {
+    int32_t n_subjects;    /* S                                                  */
+    int32_t n_trials;      /* 200                                                */
+    int32_t n_chans;       /* 30                                                 */
+    int32_t trial_len;     /* 10000 raw samples per trial                        */
+    int32_t down;          /* decimation factor fs_orig/fs_target (5)            */
+    int32_t n_taps;        /* 2*10*down+1 = 101 (scipy.signal.resample_poly)     */
+    int32_t n_sections;    /* biquads in the SOS cascade (5)                     */
+    int32_t n_sub;         /* epochs per trial (4)                               */
+    int32_t raw_is_f64;    /* 0: raw is float32, 1: raw is float64               */
+    int32_t reserved;
+} eav_preproc_cfg;
+
+size_t eav_preproc_workspace_bytes(const eav_preproc_cfg *cfg);
+
+/*
+ * raw      device  [S][n_trials][n_chans][trial_len]  f32 (or f64): the .mat memory
+ *                  order of `seg` (Dataload_eeg.py:70-82).  Per (subject, channel)
+ *                  the trials form ONE continuous sequence (Dataload_eeg.py:94).
+ * taps     host    [n_taps] f64   firwin(2*10*down+1, 1/down, ('kaiser',5.0))
+ * sos      host    [n_sections][6] f64   butter(5, band, 'bandpass', fs, 'sos')
+ * epoch_slot device [S][n_trials] i32: output slot (in units of trials, i.e. the
+ *                  first of its n_sub epochs is epoch n_sub*slot) of a kept trial,
+ *                  or -1 for a trial that segment_and_select_classes drops.
+ * epochs   device  [S][n_epochs_out][n_chans][trial_len/down/n_sub] f32
+ *                  (the model's (N,1,Chans,Samples) layout), n_epochs_out per subject.
+ * dec_out  device  optional (may be NULL) [S][n_chans][n_trials*trial_len/down] f32:
+ *                  also returns the decimated sequence (the reference's self.seg
+ *                  after downsampling(), Dataload_eeg.py:102).
+ */
+int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, const double *taps,
+                    const double *sos, const int32_t *epoch_slot, int32_t n_epochs_out,
+                    float *epochs, float *dec_out, void *workspace, size_t workspace_bytes,
+                    void *stream);
+
+/* ------------------------------------------------------------------------- */
+/* EEGNet: CNN_torch/EEGNet_tor.py:15-67 (variant 0) and CNN_torch/CNN_EEG.py:7-67
+ * (variant 1).  `n_models` independent models (one per subject) are advanced by
+ * the same launches; sample n = m*batch + b belongs to model m.               */
+/* ------------------------------------------------------------------------- */
+#define EAV_VARIANT_TOR 0   /* EEGNet_tor: ELU after BN1, full (1,K2) conv, softmax output */
+#define EAV_VARIANT_CNN 1   /* CNN_EEG.EEGNet: no ELU after BN1, depthwise+pointwise, logits */
+
+#define EAV_DROPOUT_NONE  0 /* eval mode or p == 0                                 */
+#define EAV_DROPOUT_MASK  1 /* caller supplies keep-masks (uint8 1/0): parity mode */
+#define EAV_DROPOUT_PHILOX 2/* on-device Philox4x32-10 keyed by (seed, element)   */
+
+typedef struct eav_eegnet_cfg {
+    int32_t n_models;      /* M                                                  */
+    int32_t batch;         /* B samples per model                                */
+    int32_t chans;         /* Chans   (30)                                       */
+    int32_t samples;       /* Samples (500)                                      */
+    int32_t kern_len;      /* kernLength (300)                                   */
+    int32_t F1;            /* 8                                                  */
+    int32_t D;             /* 8                                                  */
+    int32_t F2;            /* 64                                                 */
+    int32_t kern_len2;     /* 16                                                 */
+    int32_t pool1;         /* 4                                                  */
+    int32_t pool2;         /* 8                                                  */
+    int32_t n_classes;     /* nb_classes                                         */
+    int32_t variant;       /* EAV_VARIANT_*                                      */
+    int32_t bn_train;      /* 1: batch statistics + running-stat update; 0: running stats */
+    int32_t dropout_mode;  /* EAV_DROPOUT_*                                      */
+    int32_t param_stride;  /* floats between consecutive models in params/grads/m/v (>= n_params) */
+    int32_t bn_stride;     /* floats between consecutive models in bn_state (>= 2*(F1+F1*D+F2)) */
+    float   dropout_p;     /* dropoutRate                                        */
+    float   bn_eps;        /* 1e-5                                               */
+    float   bn_momentum;   /* 0.1                                                */
+    float   norm_rate;     /* max-norm of the forward hooks (variant 0); <= 0 disables */
+    uint64_t seed;         /* Philox key (EAV_DROPOUT_PHILOX)                    */
+    uint64_t step;         /* Philox stream position: change every step          */
+} eav_eegnet_cfg;
+
+/* Number of parameters of one model and the offsets (in floats) of its tensors inside
+ * a model's slice of the flat arena, in the reference's construction order
+ * (EEGNet_tor.py:24-43 / CNN_EEG.py:20-55).  offsets must hold 12 entries:
+ *   variant 0: W1 g1 b1 W2 g2 b2 W3 g3 b3 Wd bd (11 used)
+ *   variant 1: W1 g1 b1 W2 g2 b2 W3dw W3pw g3 b3 Wc bc (12 used)
+ * Returns n_params, or a negative error. */
+int64_t eav_eegnet_param_layout(const eav_eegnet_cfg *cfg, int64_t *offsets);
+
+size_t eav_eegnet_workspace_bytes(const eav_eegnet_cfg *cfg);
+
+/* Inspection hook for tests/profilers: byte offsets inside the workspace of the saved
+ * activations and backward scratch, in this order (16 entries):
+ *   y1 y2 d1 y3d y3 feat probs dz  dz3 dd1 dy3d dz2 dz1  bnf1 bnf2 bnf3
+ * (y1 [N][F1][C][T] raw conv output, y2 [N][G][T], d1 [N][G][T/4], y3 [N][F2][T/4],
+ *  feat [N][F2*T/32]; dz* are the gradients w.r.t. the BatchNorm OUTPUTS). */
+int eav_eegnet_workspace_offsets(const eav_eegnet_cfg *cfg, size_t *offsets16);
+
+/*
+ * Forward (EEGNet_tor.py:50-67 / CNN_EEG.py:57-67).
+ * x        device [n_rows][chans][samples] f32 -- the resident dataset (or the batch)
+ * x_index  device [M*B] i32 or NULL: row of x used by sample n (NULL = row n).
+ * params   device [M][param_stride] f32.  NOT const: variant 0 applies the max-norm
+ *          forward hooks (EEGNet_tor.py:33-34,47-48) after the layer used W_old.
+ * bn_state device [M][bn_stride] f32: rm1 rv1 rm2 rv2 rm3 rv3 (updated when bn_train).
+ * mask1    device [M*B][F1*D][samples/pool1] u8 keep-mask (EAV_DROPOUT_MASK) or NULL
+ * mask2    device [M*B][F2][samples/pool1/pool2] u8 keep-mask or NULL
+ * out      device [M*B][n_classes] f32: probabilities (variant 0) / logits (variant 1)
+ * workspace: saved activations for eav_eegnet_backward (same cfg, same buffers).
+ */
+int eav_eegnet_forward(const eav_eegnet_cfg *cfg, const float *x, const int32_t *x_index,
+                       float *params, float *bn_state, const uint8_t *mask1,
+                       const uint8_t *mask2, float *out, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/*
+ * nn.CrossEntropyLoss()(out, targets) per model (EEGNet_tor.py:81,105) and its
+ * gradient w.r.t. `out`.
+ * targets  device [n_rows] i64 class indices, addressed through x_index like x.
+ * loss     device [M] f32: mean over the model's batch.
+ * dout     device [M*B][n_classes] f32 (may be NULL: loss only).
+ * n_correct device [M] i32 (may be NULL): #samples whose argmax(out) == target.
+ */
+int eav_eegnet_loss(const eav_eegnet_cfg *cfg, const float *out, const int64_t *targets,
+                    const int32_t *x_index, float *loss, float *dout, int32_t *n_correct,
+                    void *stream);
+
+/*
+ * Backward of eav_eegnet_forward given d(loss)/d(out).
+ * grads    device [M][param_stride] f32, every parameter's gradient is overwritten.
+ */
+int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, const int32_t *x_index,
+                        const float *params, const float *dout, const uint8_t *mask1,
+                        const uint8_t *mask2, float *grads, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/*
+ * torch.optim.Adam step (EEGNet_tor.py:82,110; betas/eps/no weight decay as there)
+ * over a flat arena of n floats: m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g;
+ * p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ * step_count is t (1-based, already incremented by the caller).
+ */
+int eav_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                  int64_t n, int64_t step_count, float lr, float beta1, float beta2,
+                  float eps, void *stream);
+
+/* torch.renorm(p=2, dim=0, maxnorm) in place over `n_rows` rows of `row_len` floats
+ * spaced `row_stride` apart (the max-norm hook body, EEGNet_tor.py:34,48). */
+int eav_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_stride,
+                    float maxnorm, void *stream);
+
+/* Measured-peak helper for bench.py: runs a register-resident FFMA loop on every SM
+ * and returns the achieved fp32 TFLOP/s (host-synchronous; not part of the hot path). */
+int eav_measure_fp32_peak(double *tflops, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAV_B200_H_ */

@@ -1,0 +1,225 @@
+"""-m gpu parity tests of the EEGNet CUDA path (through the C ABI) against golden vectors
+produced by the unmodified reference and against the CPU oracle.
+Tolerance (BASELINE.json north_star): probabilities / logits, every gradient and the loss
+within 1e-4 relative in fp32."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _setup(golden, name, variant=0, **dims_kw):
+    from eav_b200.ops import EegnetDims
+    import gpu_util as U
+    g = golden(name)
+    sd = U.init_from_golden(g)
+    return g, sd, U
+
+
+def _tor_dims():
+    from eav_b200.ops import EegnetDims
+    return EegnetDims(5)
+
+
+@pytest.mark.parametrize("tag", ["b8", "b8_renorm"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_tor_fwd_bwd_vs_reference(golden, tag, mode):
+    from eav_b200.ops import EegnetEngine
+    g, sd, U = _setup(golden, f"eegnet_tor_{tag}.npz")
+    dims = _tor_dims()
+    train = mode == "train"
+    x = torch.from_numpy(g["x"]).cuda().reshape(8, 30, 500).contiguous()
+    y = torch.from_numpy(g["y"]).cuda()
+    params, bn = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+    m1 = torch.from_numpy(g["mask1"]).cuda().reshape(8, 64, 125).contiguous() if train else None
+    m2 = torch.from_numpy(g["mask2"]).cuda().reshape(8, 64, 15).contiguous() if train else None
+    eng = EegnetEngine(dims, 1, 8)
+    out = eng.forward(x, params, bn, bn_train=train, mask1=m1, mask2=m2)
+    loss, dout, ncorrect = eng.loss(out, y)
+    grads = eng.backward(x, params, dout, mask1=m1, mask2=m2)
+    torch.cuda.synchronize()
+
+    # localise: layer-by-layer activations against the CPU oracle
+    masks = [torch.from_numpy(g["mask1"]), torch.from_numpy(g["mask2"])] if train else None
+    inter = U.oracle_intermediates_tor(sd, torch.from_numpy(g["x"]), train, masks)
+    for k in ("y1", "y2", "d1", "y3", "feat"):
+        got = eng.saved(k).cpu().numpy().reshape(inter[k].shape)
+        assert U.rel_l2(got, inter[k].numpy()) < 2e-5, f"activation {k}"
+
+    assert U.rel_max(out.cpu().numpy(), g[f"{mode}::probs"]) < TOL
+    assert abs(float(loss[0]) - float(g[f"{mode}::loss"])) < TOL * abs(float(g[f"{mode}::loss"]))
+    assert int(ncorrect[0]) == int((g[f"{mode}::probs"].argmax(1) == g["y"]).sum())
+    gd = U.unpack(dims, grads[0])
+    for k, v in gd.items():
+        ref = g[f"{mode}::grad::{k}"]
+        assert U.rel_l2(v.numpy(), ref) < TOL, f"grad {k}: {U.rel_l2(v.numpy(), ref)}"
+        assert U.rel_max(v.numpy(), ref) < 5 * TOL, f"grad {k} (max)"
+    # side effects: running statistics, max-norm hooks on the weights
+    after_p, after_bn = U.unpack(dims, params[0]), U.unpack_bn(dims, bn[0])
+    for k in g.files:
+        if k.startswith(f"{mode}::after::") and "num_batches" not in k:
+            name = k.split("::")[-1]
+            mine = after_p[name] if name in after_p else after_bn[name]
+            assert np.allclose(mine.numpy(), g[k], rtol=1e-5, atol=1e-6), name
+
+
+def test_tor_multi_model_ragged_batch_and_index(golden):
+    """3 independent models in one launch, B=5 (odd, exercises the pair tail), rows gathered by index."""
+    import eegnet_oracle as EO
+    from eav_b200.ops import EegnetEngine
+    g, sd0, U = _setup(golden, "eegnet_tor_b8.npz")
+    dims = _tor_dims()
+    gen = torch.Generator().manual_seed(5)
+    M, B, R = 3, 5, 40
+    sds = []
+    for m in range(M):
+        sd = {k: (v.clone() if v.dtype != torch.float32 else v + 0.05 * m * torch.randn(v.shape, generator=gen)) for k, v in sd0.items()}
+        for bnn in U.TOR_BN:
+            sd[bnn + ".running_var"] = sd[bnn + ".running_var"].abs() + 0.5
+        sds.append(sd)
+    data = torch.randn(R, 30, 500, generator=gen)
+    labels = torch.randint(0, 5, (R,), generator=gen)
+    idx = torch.randint(0, R, (M * B,), generator=gen).int()
+    for train in (False, True):
+        params, bn = U.pack_params(dims, sds), U.pack_bn(dims, sds)
+        m1 = (torch.rand(M * B, 64, 125, generator=gen) > 0.5).to(torch.uint8)
+        m2 = (torch.rand(M * B, 64, 15, generator=gen) > 0.5).to(torch.uint8)
+        eng = EegnetEngine(dims, M, B)
+        out = eng.forward(data.cuda(), params, bn, bn_train=train, x_index=idx.cuda(),
+                          mask1=m1.cuda() if train else None, mask2=m2.cuda() if train else None)
+        loss, dout, _ = eng.loss(out, labels.cuda(), x_index=idx.cuda())
+        grads = eng.backward(data.cuda(), params, dout, x_index=idx.cuda(),
+                             mask1=m1.cuda() if train else None, mask2=m2.cuda() if train else None)
+        torch.cuda.synchronize()
+        for m in range(M):
+            p, b = EO.split_state(sds[m], "tor")
+            rows = idx[m * B:(m + 1) * B].long()
+            xm, ym = data[rows].unsqueeze(1), labels[rows]
+            masks = [m1[m * B:(m + 1) * B].unsqueeze(2), m2[m * B:(m + 1) * B].unsqueeze(2)] if train else None
+            o = EO.tor_forward(p, b, xm, train, masks=masks)
+            l = EO.loss_fn(o, ym)
+            l.backward()
+            assert U.rel_max(out[m * B:(m + 1) * B].cpu().numpy(), o.detach().numpy()) < TOL
+            assert abs(float(loss[m]) - float(l)) < TOL * float(l)
+            gd = U.unpack(dims, grads[m])
+            for k in EO.TOR_PARAMS:
+                assert U.rel_l2(gd[k].numpy(), p[k].grad.numpy()) < TOL, (train, m, k)
+
+
+@pytest.mark.parametrize("B", [32, 24, 16])
+def test_tor_batch_sizes_vs_oracle(golden, B):
+    """B=32 and the ragged last batches 24 / 16 (drop_last=False), both BN modes."""
+    import eegnet_oracle as EO
+    from eav_b200.ops import EegnetEngine
+    g, sd, U = _setup(golden, "eegnet_tor_b8.npz")
+    dims = _tor_dims()
+    gen = torch.Generator().manual_seed(B)
+    x = torch.randn(B, 30, 500, generator=gen)
+    y = torch.randint(0, 5, (B,), generator=gen)
+    for train in (True, False):
+        m1 = (torch.rand(B, 64, 125, generator=gen) > 0.5).to(torch.uint8)
+        m2 = (torch.rand(B, 64, 15, generator=gen) > 0.5).to(torch.uint8)
+        params, bn = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+        eng = EegnetEngine(dims, 1, B)
+        out = eng.forward(x.cuda(), params, bn, bn_train=train, mask1=m1.cuda() if train else None,
+                          mask2=m2.cuda() if train else None)
+        loss, dout, _ = eng.loss(out, y.cuda())
+        grads = eng.backward(x.cuda(), params, dout, mask1=m1.cuda() if train else None,
+                             mask2=m2.cuda() if train else None)
+        p, b = EO.split_state(sd, "tor")
+        o = EO.tor_forward(p, b, x.unsqueeze(1), train, masks=[m1.unsqueeze(2), m2.unsqueeze(2)] if train else None)
+        l = EO.loss_fn(o, y)
+        l.backward()
+        assert U.rel_max(out.cpu().numpy(), o.detach().numpy()) < TOL
+        assert abs(float(loss[0]) - float(l)) < TOL * float(l)
+        gd = U.unpack(dims, grads[0])
+        for k in EO.TOR_PARAMS:
+            assert U.rel_l2(gd[k].numpy(), p[k].grad.numpy()) < TOL, (train, k)
+
+
+def test_adam_trajectory_vs_reference(golden):
+    import golden_inputs as GI
+    from eav_b200 import ops
+    g, sd, U = _setup(golden, "eegnet_tor_adam6.npz")
+    dims = _tor_dims()
+    xs, ys = GI.adam6_inputs()
+    assert np.allclose(GI.checksum(xs.numpy(), ys.numpy()), g["input_checksum"], rtol=1e-12)
+    params, bn = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+    m, v = torch.zeros_like(params), torch.zeros_like(params)
+    eng = ops.EegnetEngine(dims, 1, 8)
+    losses = []
+    for i in range(6):
+        train = i < 2
+        m1 = torch.from_numpy(g["masks1"][i]).cuda().reshape(8, 64, 125).contiguous() if train else None
+        m2 = torch.from_numpy(g["masks2"][i]).cuda().reshape(8, 64, 15).contiguous() if train else None
+        x = xs[i].reshape(8, 30, 500).contiguous().cuda()
+        out = eng.forward(x, params, bn, bn_train=train, mask1=m1, mask2=m2)
+        loss, dout, _ = eng.loss(out, ys[i].cuda())
+        grads = eng.backward(x, params, dout, mask1=m1, mask2=m2)
+        ops.adam_step(params, grads, m, v, i + 1, 1e-3)
+        losses.append(float(loss[0]))
+    assert np.abs(np.array(losses) - g["losses"]).max() < TOL * np.abs(g["losses"]).max()
+    final = U.unpack(dims, params[0])
+    for k, t in final.items():
+        assert np.abs(t.numpy() - g[f"final::{k}"]).max() < 2e-3, k     # sign-like first Adam steps
+
+
+@pytest.mark.parametrize("tag", ["default", "eav"])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_cnn_eeg_fwd_bwd_vs_reference(golden, tag, mode):
+    from eav_b200.ops import EegnetDims, EegnetEngine
+    from eav_b200._lib import EAV_VARIANT_CNN
+    g, sd, U = _setup(golden, f"cnn_eeg_{tag}.npz")
+    if tag == "default":
+        dims = EegnetDims(4, Chans=64, Samples=128, dropoutRate=0.25, kernLength=64, F1=8, D=2, F2=16, variant=EAV_VARIANT_CNN)
+    else:
+        dims = EegnetDims(5, Chans=30, Samples=500, dropoutRate=0.5, kernLength=300, F1=8, D=8, F2=64, variant=EAV_VARIANT_CNN)
+    train = mode == "train"
+    B = g["x"].shape[0]
+    x = torch.from_numpy(g["x"]).cuda().contiguous()
+    y = torch.from_numpy(g["y"]).cuda()
+    params, bn = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+    G, T4 = dims.F1 * dims.D, dims.Samples // 4
+    m1 = torch.from_numpy(g["mask1"]).cuda().reshape(B, G, T4).contiguous() if train else None
+    m2 = torch.from_numpy(g["mask2"]).cuda().reshape(B, dims.F2, T4 // 8).contiguous() if train else None
+    eng = EegnetEngine(dims, 1, B)
+    out = eng.forward(x, params, bn, bn_train=train, mask1=m1, mask2=m2)
+    loss, dout, _ = eng.loss(out, y)
+    grads = eng.backward(x, params, dout, mask1=m1, mask2=m2)
+    assert U.rel_max(out.cpu().numpy(), g[f"{mode}::logits"]) < TOL
+    assert abs(float(loss[0]) - float(g[f"{mode}::loss"])) < TOL * float(g[f"{mode}::loss"])
+    gd = U.unpack(dims, grads[0])
+    for k, v in gd.items():
+        ref = g[f"{mode}::grad::{k}"]
+        # BN1's affine gradient is analytically ~0 in train mode (it feeds BN2 linearly): absolute floor
+        assert U.rel_l2(v.numpy(), ref) < TOL or np.abs(v.numpy() - ref).max() < 5e-6, f"grad {k}"
+
+
+def test_philox_dropout_is_consistent_between_forward_and_backward(golden):
+    """On-device dropout: keep-rate ~ 1-p, deterministic in (seed, step), and backward uses the
+    same mask as forward (checked by replaying the derived mask through the explicit-mask path)."""
+    from eav_b200.ops import EegnetEngine
+    g, sd, U = _setup(golden, "eegnet_tor_b8.npz")
+    dims = _tor_dims()
+    x = torch.from_numpy(g["x"]).cuda().reshape(8, 30, 500).contiguous()
+    y = torch.from_numpy(g["y"]).cuda()
+    eng = EegnetEngine(dims, 1, 8)
+    params, bn = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+    out = eng.forward(x, params, bn, bn_train=True, philox=(1234, 7))
+    _, dout, _ = eng.loss(out, y)
+    g_ph = eng.backward(x, params, dout).clone()
+    d1, feat = eng.saved("d1").clone(), eng.saved("feat").clone()
+    m1 = (d1 != 0).to(torch.uint8).contiguous()
+    m2 = (feat != 0).to(torch.uint8).reshape(8, 64, 15).contiguous()
+    assert 0.45 < m1.float().mean().item() < 0.55 and 0.4 < m2.float().mean().item() < 0.6
+    params2, bn2 = U.pack_params(dims, [sd]), U.pack_bn(dims, [sd])
+    out2 = eng.forward(x, params2, bn2, bn_train=True, mask1=m1, mask2=m2)
+    _, dout2, _ = eng.loss(out2, y)
+    g_mk = eng.backward(x, params2, dout2, mask1=m1, mask2=m2)
+    assert torch.equal(out, out2)
+    assert torch.allclose(g_ph, g_mk, rtol=0, atol=0)
+    out3 = eng.forward(x, U.pack_params(dims, [sd]), U.pack_bn(dims, [sd]), bn_train=True, philox=(1234, 8))
+    assert not torch.equal(out, out3)

@@ -1,0 +1,136 @@
+"""-m gpu parity tests of the preprocessing CUDA path (FIR decimate -> SOS scan -> epoch
+scatter, through the C ABI) against the reference's golden vectors and the CPU oracle.
+Gate: epochs within 1e-5 of the per-channel RMS of the reference's float64
+result; epoch / label indexing bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _slots(keep):
+    """epoch_slot for one subject: running index over kept trials, -1 for dropped ones."""
+    slot = np.full(keep.shape, -1, dtype=np.int32)
+    slot[keep] = np.arange(int(keep.sum()), dtype=np.int32)
+    return slot
+
+
+def _chan_rel_err(got, ref):
+    """max over channels of max|got-ref| / rms(ref) ; arrays [epochs][ch][t]"""
+    rms = np.sqrt((ref.astype(np.float64) ** 2).mean(axis=(0, 2)))
+    err = np.abs(got.astype(np.float64) - ref).max(axis=(0, 2))
+    return float((err / rms).max())
+
+
+def test_small_case_vs_reference_golden(golden):
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    g = golden("preproc_small.npz")
+    raw = g["raw"]                                     # [6 trials][4 ch][1000]
+    n_tr, n_ch, tl = raw.shape
+    eng = PreprocEngine(1, n_trials=n_tr, n_chans=n_ch, trial_len=tl)
+    keep = np.ones(n_tr, dtype=bool)
+    slot = torch.from_numpy(_slots(keep)[None]).cuda()
+    taps = O.decimation_taps(5)
+    for tag, band in (("b0545", [0.5, 45]), ("b0530", [5, 30])):
+        sos = O.butter_sos(band, 100.0)
+        ep, dec = eng.run(torch.from_numpy(raw[None]).cuda(), taps, sos, slot, 4 * n_tr, want_dec=True)
+        ref_dec = np.transpose(g["dec"], (0, 2, 1)).reshape(n_ch, -1)          # (ch, trials*t)
+        d = dec[0].cpu().numpy()
+        assert np.abs(d - ref_dec).max() / np.sqrt((ref_dec ** 2).mean()) < 2e-6
+        ref = g["filt_" + tag]                                                # (ch, 200, trials)
+        ref_ep = np.transpose(ref, (2, 0, 1)).reshape(n_tr, n_ch, 4, 50).transpose(0, 2, 1, 3).reshape(4 * n_tr, n_ch, 50)
+        assert _chan_rel_err(ep[0].cpu().numpy(), ref_ep) < TOL, tag
+
+
+def test_generic_decimation_factor_vs_oracle():
+    """down=4 (81 taps) goes through the generic FIR kernel; 3 biquads through another SOS instantiation."""
+    import eeg_oracle as O
+    from scipy.signal import butter
+    from eav_b200.ops import PreprocEngine
+    rng = np.random.default_rng(3)
+    raw = rng.standard_normal((5, 3, 800)).astype(np.float32) + 2.0
+    taps = O.decimation_taps(4)
+    sos = np.ascontiguousarray(butter(3, [1, 40], btype="bandpass", fs=125.0, output="sos"))
+    eng = PreprocEngine(1, n_trials=5, n_chans=3, trial_len=800, down=4, n_taps=81, n_sections=3, n_sub=4)
+    keep = np.array([1, 0, 1, 1, 0], dtype=bool)
+    ep, dec = eng.run(torch.from_numpy(raw[None]).cuda(), taps, sos, torch.from_numpy(_slots(keep)[None]).cuda(),
+                      4 * 3, want_dec=True)
+    ref_dec = O.fir_decimate(raw, taps, 4)
+    assert np.abs(dec[0].cpu().numpy() - ref_dec).max() < 2e-6 * np.abs(ref_dec).max()
+    filt = O.sosfilt(sos, ref_dec).reshape(3, 5, 4, 50)                       # ch, trial, sub, t
+    ref_ep = filt[:, keep].transpose(1, 2, 0, 3).reshape(12, 3, 50)
+    assert _chan_rel_err(ep[0].cpu().numpy(), ref_ep) < TOL
+
+
+@pytest.fixture(scope="module")
+def subject_pair():
+    import eeg_oracle as O
+    raws, labels = zip(*[O.synth_subject(s) for s in (1, 2)])
+    return np.stack(raws), labels
+
+
+def test_dataset_shaped_subjects_vs_oracle_and_reference_digest(golden, subject_pair):
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    raws, labels = subject_pair
+    g = golden("preproc_subject1_digest.npz")
+    taps, sos = O.decimation_taps(5), O.butter_sos([0.5, 45], 100.0)
+    plans = [O.epoch_plan(l) for l in labels]
+    slot = np.stack([_slots(p[0]) for p in plans])
+    eng = PreprocEngine(2)
+    ep = eng.run(torch.from_numpy(raws).cuda(), taps, sos, torch.from_numpy(slot).cuda(), 400).cpu().numpy()
+    assert ep.shape == (2, 400, 30, 500)
+    # labels / epoch order are host integer logic: bit-exact against the reference
+    assert np.array_equal(plans[0][1], g["y"])
+    # subject 1 against the reference's own output (strided sample + per-epoch sums + channel RMS)
+    rms = g["x_chan_rms"]
+    sub = ep[0][::25, ::7, ::20]
+    assert (np.abs(sub - g["x_sub"]).max(axis=(0, 2)) / rms[::7]).max() < TOL
+    assert np.abs(ep[0].astype(np.float64).sum(axis=(1, 2)) - g["x_epoch_sum"]).max() < 1e-2
+    # both subjects against the full CPU oracle
+    for s in range(2):
+        xo, yo = O.prepare_data(raws[s], labels[s], [0.5, 45])
+        assert _chan_rel_err(ep[s], xo) < TOL, s
+
+
+def test_properties_at_full_size(subject_pair):
+    """Size-independent properties at the dataset shape: exact homogeneity under power-of-two
+    scaling, and independence of a kept epoch from WHICH other trials are kept (the filter is
+    continuous over all trials, SURVEY F8, so dropping trials must not change survivors)."""
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    raws, labels = subject_pair
+    taps, sos = O.decimation_taps(5), O.butter_sos([5, 30], 100.0)
+    keep = O.epoch_plan(labels[0])[0]
+    eng = PreprocEngine(1)
+    raw = torch.from_numpy(raws[:1]).cuda()
+    a = eng.run(raw, taps, sos, torch.from_numpy(_slots(keep)[None]).cuda(), 400).clone()
+    b = eng.run(raw * 4.0, taps, sos, torch.from_numpy(_slots(keep)[None]).cuda(), 400).clone()
+    assert torch.equal(a * 4.0, b)
+    allk = np.ones(200, dtype=bool)
+    c = eng.run(raw, taps, sos, torch.from_numpy(_slots(allk)[None]).cuda(), 800)
+    kept_idx = np.nonzero(keep)[0]
+    sel = (kept_idx[:, None] * 4 + np.arange(4)[None]).reshape(-1)
+    assert torch.equal(c[0, torch.from_numpy(sel).cuda()], a[0])
+    # a constant record decimates to the same constant away from the record edges (sum h == 1)
+    const = torch.full((1, 200, 30, 10000), 3.25, device="cuda")
+    _, dec = eng.run(const, taps, sos, torch.from_numpy(_slots(keep)[None]).cuda(), 400, want_dec=True)
+    assert (dec[0, :, 20:-20] - 3.25).abs().max().item() < 1e-6
+
+
+def test_empty_selection_and_errors():
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    eng = PreprocEngine(1, n_trials=4, n_chans=2, trial_len=1000)
+    raw = torch.randn(1, 4, 2, 1000, device="cuda")
+    slot = torch.full((1, 4), -1, dtype=torch.int32, device="cuda")
+    ep = eng.run(raw, O.decimation_taps(5), O.butter_sos([5, 30], 100.0), slot, 0)
+    assert ep.shape == (1, 0, 2, 50)
+    with pytest.raises(RuntimeError, match="multiple of n_sub"):
+        eng.run(raw, O.decimation_taps(5), O.butter_sos([5, 30], 100.0), slot, 3)
+    with pytest.raises(RuntimeError):
+        eng.run(raw.cpu(), O.decimation_taps(5), O.butter_sos([5, 30], 100.0), slot, 0)
