@@ -28,13 +28,14 @@ class EegnetCfg(Structure):
                                         "kern_len2", "pool1", "pool2", "n_classes", "variant", "bn_train",
                                         "dropout_mode", "param_stride", "bn_stride")]
                 + [(n, c_float) for n in ("dropout_p", "bn_eps", "bn_momentum", "norm_rate")]
-                + [("seed", c_uint64), ("step", c_uint64)])
+                + [("seed", c_uint64), ("step", c_uint64), ("step_device_ptr", c_uint64)])
 
 
 # every symbol include/eav_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "eav_last_error_string": (c_char_p, []),
     "eav_abi_version": (c_int, []),
+    "eav_launch_count": (c_uint64, []),
     "eav_check_device": (c_int, []),
     "eav_preproc_workspace_bytes": (c_size_t, [POINTER(PreprocCfg)]),
     "eav_preproc_run": (c_int, [POINTER(PreprocCfg), c_void_p, POINTER(c_double), POINTER(c_double), c_void_p,
@@ -48,8 +49,15 @@ SYMBOLS = {
                                 c_void_p]),
     "eav_eegnet_backward": (c_int, [POINTER(EegnetCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "eav_eegnet_stage_count": (c_int, []),
+    "eav_eegnet_stage_forward_end": (c_int, []),
+    "eav_eegnet_stage_name": (c_char_p, [c_int]),
+    "eav_eegnet_run_stage": (c_int, [POINTER(EegnetCfg), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "eav_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float,
                               c_float, c_void_p]),
+    "eav_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
+                                    c_float, c_float, c_void_p]),
     "eav_renorm_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
 }

@@ -8,6 +8,8 @@
 namespace eav {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -35,6 +37,7 @@ int make_dims(const eav_eegnet_cfg *c, NetDims *d) {
     d->pad1l = (d->K1 - 1) / 2; d->pad2l = (d->K2 - 1) / 2;   // torch padding='same': left = total//2
     d->p_drop = c->dropout_p; d->eps = c->bn_eps; d->momentum = c->bn_momentum; d->norm_rate = c->norm_rate;
     d->seed = c->seed; d->step = c->step;
+    d->step_ptr = reinterpret_cast<const unsigned long long *>(c->step_device_ptr);
     if (d->p_drop == 0.f) d->dropout_mode = EAV_DROPOUT_NONE;
     int64_t o = 0;
     d->oW1 = o; o += (int64_t)d->F1 * d->K1;
@@ -114,6 +117,7 @@ using namespace eav;
 
 extern "C" const char *eav_last_error_string(void) { return g_err; }
 extern "C" int eav_abi_version(void) { return EAV_ABI_VERSION; }
+extern "C" uint64_t eav_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int eav_check_device(void) {
     int dev = 0;
@@ -167,38 +171,131 @@ extern "C" int eav_eegnet_workspace_offsets(const eav_eegnet_cfg *cfg, size_t *o
 #define WS(T, off) reinterpret_cast<T *>(reinterpret_cast<char *>(workspace) + (off))
 #define TRY(call) do { int rc__ = (call); if (rc__) return rc__; } while (0)
 
+// ---------------------------------------------------------------------------------
+// Stage table.  forward = stages [0, EAV_STAGE_FWD_END), backward = [EAV_STAGE_FWD_END,
+// EAV_STAGE_COUNT).  eav_eegnet_run_stage() launches exactly one of them on the buffers
+// a previous full pass left in the workspace (per-kernel timing / profiling hook).
+// ---------------------------------------------------------------------------------
+enum {
+    ST_TCONV_FWD = 0, ST_BN1, ST_DW_FWD, ST_RENORM_W2, ST_BN2, ST_POOL1_FWD, ST_SEPCONV_FWD, ST_BN3,
+    ST_TAIL_FWD, ST_RENORM_WD,
+    ST_TAIL_BWD, ST_DENSE_BWD_W, ST_BN3_BWD, ST_SEPCONV_BWD_DX, ST_SEPCONV_BWD_DW, ST_POOL1_BWD, ST_BN2_BWD,
+    ST_DW_BWD, ST_BN1_BWD, ST_TCONV_BWD_DW, ST_COUNT
+};
+static const int ST_FWD_END = ST_TAIL_BWD;
+static const char *kStageNames[ST_COUNT] = {
+    "tconv_fwd", "bn1_finalize", "dw_fwd", "renorm_depthwise", "bn2_finalize", "pool1_fwd", "sepconv_fwd",
+    "bn3_finalize", "tail_fwd", "renorm_dense",
+    "tail_bwd", "dense_bwd_w", "bn3_bwd_finalize", "sepconv_bwd_dx", "sepconv_bwd_dw", "pool1_bwd",
+    "bn2_bwd_finalize", "dw_bwd", "bn1_bwd_finalize", "tconv_bwd_dw"};
+
+struct StageArgs {
+    const float *x; const int32_t *x_index; float *params; float *bn_state; const uint8_t *mask1, *mask2;
+    float *out; const float *dout; float *grads; void *workspace;
+};
+
+static int run_stage(const NetDims &d, const WsLayout &w, int stage, const StageArgs &a, cudaStream_t st) {
+    void *workspace = a.workspace;
+    float *part = WS(float, w.part);
+    float *pstat = d.bn_train ? part : nullptr;
+    float *partw = WS(float, w.partw);
+    const bool tor = d.variant == EAV_VARIANT_TOR;
+    // rows of BatchNorm partial sums each producer writes per model
+    const int rows1 = d.B * cdiv(d.C, 4) * cdiv(d.T, 512);
+    const int rows2 = d.B * cdiv(d.T, 128);
+    const int rows3 = tor ? cdiv(d.B, 2) * cdiv(d.T4, 128) : d.B;
+    switch (stage) {
+        case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.y1), pstat, nullptr, st);
+        case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, (double)d.B * d.C * d.T, a.params, a.bn_state, WS(float4, w.bnf1), st);
+        case ST_DW_FWD: return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, st);
+        case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34)
+            if (tor && d.norm_rate > 0.f)
+                return launch_renorm_rows(a.params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st);
+            return 0;
+        case ST_BN2: return launch_bn_finalize(d, 2, part, rows2, (double)d.B * d.T, a.params, a.bn_state, WS(float4, w.bnf2), st);
+        case ST_POOL1_FWD: return launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.d1), st);
+        case ST_SEPCONV_FWD:
+            if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3), pstat, nullptr, st);
+            TRY(launch_dwt_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3d), st));
+            return launch_pw_fwd(d, WS(float, w.y3d), a.params, WS(float, w.y3), pstat, nullptr, st);
+        case ST_BN3: return launch_bn_finalize(d, 3, part, rows3, (double)d.B * d.T4, a.params, a.bn_state, WS(float4, w.bnf3), st);
+        case ST_TAIL_FWD:
+            return launch_tail_fwd(d, WS(float, w.y3), WS(float4, w.bnf3), a.mask2, a.params, WS(float, w.feat), a.out, WS(float, w.probs), st);
+        case ST_RENORM_WD:   // hook on dense (EEGNet_tor.py:47-48)
+            if (tor && d.norm_rate > 0.f)
+                return launch_renorm_rows(a.params + d.oWd, (int64_t)d.M * d.NC, d.FEAT, d.FEAT, d.NC, d.pstride, d.norm_rate, st);
+            return 0;
+        case ST_TAIL_BWD:
+            return launch_tail_bwd(d, a.dout, WS(float, w.probs), a.params, WS(float, w.y3), WS(float4, w.bnf3), a.mask2,
+                                   WS(float, w.dz), WS(float, w.dz3), part, st);
+        case ST_DENSE_BWD_W: return launch_dense_bwd_w(d, WS(float, w.feat), WS(float, w.dz), a.grads, st);
+        case ST_BN3_BWD:
+            return launch_bn_bwd_finalize(d, 3, part, d.B, (double)d.B * d.T4, a.params, WS(float4, w.bnf3), WS(float4, w.bnb3), a.grads, st);
+        case ST_SEPCONV_BWD_DX:
+            if (tor)
+                return launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
+                                             a.params, WS(float, w.dd1), st);
+            return launch_pw_bwd(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), WS(float, w.y3d),
+                                 a.params, WS(float, w.dy3d), partw, a.grads, st);
+        case ST_SEPCONV_BWD_DW:
+            if (tor)
+                return launch_sepconv_bwd_dw(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
+                                             WS(float, w.d1), partw, a.grads, st);
+            return launch_dwt_bwd(d, WS(float, w.dy3d), WS(float, w.d1), a.params, WS(float, w.dd1), partw, a.grads, st);
+        case ST_POOL1_BWD:
+            return launch_pool1_bwd(d, WS(float, w.dd1), WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.dz2), part, st);
+        case ST_BN2_BWD:
+            return launch_bn_bwd_finalize(d, 2, part, d.B, (double)d.B * d.T, a.params, WS(float4, w.bnf2), WS(float4, w.bnb2), a.grads, st);
+        case ST_DW_BWD:
+            return launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
+                                 WS(float4, w.bnf1), a.params, WS(float, w.dz1), partw, part, a.grads, st);
+        case ST_BN1_BWD:
+            return launch_bn_bwd_finalize(d, 1, part, d.B, (double)d.B * d.C * d.T, a.params, WS(float4, w.bnf1), WS(float4, w.bnb1), a.grads, st);
+        case ST_TCONV_BWD_DW:
+            return launch_tconv_bwd_dw(d, a.x, a.x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
+                                       partw, a.grads, st);
+        default: break;
+    }
+    set_error("run_stage: unknown stage %d", stage);
+    return EAV_ERR_BAD_ARG;
+}
+
+static int check_common(const NetDims &d, const WsLayout &w, const StageArgs &a, size_t workspace_bytes, const char *who) {
+    EAV_REQUIRE(a.x && a.params && a.workspace, EAV_ERR_BAD_ARG, "%s: null pointer", who);
+    EAV_REQUIRE(workspace_bytes >= w.total, EAV_ERR_WORKSPACE, "%s: workspace %zu < required %zu", who, workspace_bytes, w.total);
+    EAV_REQUIRE(d.dropout_mode != EAV_DROPOUT_MASK || (a.mask1 && a.mask2), EAV_ERR_BAD_ARG, "%s: dropout masks required", who);
+    return 0;
+}
+
+extern "C" int eav_eegnet_stage_count(void) { return ST_COUNT; }
+extern "C" int eav_eegnet_stage_forward_end(void) { return ST_FWD_END; }
+extern "C" const char *eav_eegnet_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
+
+extern "C" int eav_eegnet_run_stage(const eav_eegnet_cfg *cfg, int stage, const float *x, const int32_t *x_index,
+                                    float *params, float *bn_state, const uint8_t *mask1, const uint8_t *mask2,
+                                    float *out, const float *dout, float *grads, void *workspace,
+                                    size_t workspace_bytes, void *stream) {
+    NetDims d;
+    TRY(make_dims(cfg, &d));
+    const WsLayout w = make_ws_layout(d);
+    StageArgs a = {x, x_index, params, bn_state, mask1, mask2, out, dout, grads, workspace};
+    TRY(check_common(d, w, a, workspace_bytes, "eegnet_run_stage"));
+    EAV_REQUIRE(stage >= 0 && stage < ST_COUNT, EAV_ERR_BAD_ARG, "eegnet_run_stage: stage %d out of range", stage);
+    if (stage < ST_FWD_END) EAV_REQUIRE(bn_state && out, EAV_ERR_BAD_ARG, "eegnet_run_stage: forward stage needs bn_state and out");
+    else EAV_REQUIRE(dout && grads, EAV_ERR_BAD_ARG, "eegnet_run_stage: backward stage needs dout and grads");
+    return run_stage(d, w, stage, a, (cudaStream_t)stream);
+}
+
 extern "C" int eav_eegnet_forward(const eav_eegnet_cfg *cfg, const float *x, const int32_t *x_index, float *params,
                                   float *bn_state, const uint8_t *mask1, const uint8_t *mask2, float *out,
                                   void *workspace, size_t workspace_bytes, void *stream) {
     NetDims d;
     TRY(make_dims(cfg, &d));
-    EAV_REQUIRE(x && params && bn_state && out && workspace, EAV_ERR_BAD_ARG, "eegnet_forward: null pointer");
     const WsLayout w = make_ws_layout(d);
-    EAV_REQUIRE(workspace_bytes >= w.total, EAV_ERR_WORKSPACE, "eegnet_forward: workspace %zu < required %zu", workspace_bytes, w.total);
-    EAV_REQUIRE(d.dropout_mode != EAV_DROPOUT_MASK || (mask1 && mask2), EAV_ERR_BAD_ARG, "eegnet_forward: dropout masks required");
-    cudaStream_t st = (cudaStream_t)stream;
-    float *part = WS(float, w.part);
-    float *pstat = d.bn_train ? part : nullptr;
-    int rows = 0;
-
-    TRY(launch_tconv_fwd(d, x, x_index, params, WS(float, w.y1), pstat, &rows, st));
-    TRY(launch_bn_finalize(d, 1, part, rows, (double)d.B * d.C * d.T, params, bn_state, WS(float4, w.bnf1), st));
-    TRY(launch_dw_fwd(d, WS(float, w.y1), params, WS(float4, w.bnf1), WS(float, w.y2), pstat, &rows, st));
-    if (d.variant == EAV_VARIANT_TOR && d.norm_rate > 0.f)   // hook after the layer used W_old (EEGNet_tor.py:33-34)
-        TRY(launch_renorm_rows(params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st));
-    TRY(launch_bn_finalize(d, 2, part, rows, (double)d.B * d.T, params, bn_state, WS(float4, w.bnf2), st));
-    TRY(launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), mask1, WS(float, w.d1), st));
-    if (d.variant == EAV_VARIANT_TOR) {
-        TRY(launch_sepconv_fwd(d, WS(float, w.d1), params, WS(float, w.y3), pstat, &rows, st));
-    } else {
-        TRY(launch_dwt_fwd(d, WS(float, w.d1), params, WS(float, w.y3d), st));
-        TRY(launch_pw_fwd(d, WS(float, w.y3d), params, WS(float, w.y3), pstat, &rows, st));
-    }
-    TRY(launch_bn_finalize(d, 3, part, rows, (double)d.B * d.T4, params, bn_state, WS(float4, w.bnf3), st));
-    TRY(launch_tail_fwd(d, WS(float, w.y3), WS(float4, w.bnf3), mask2, params, WS(float, w.feat), out,
-                        WS(float, w.probs), st));
-    if (d.variant == EAV_VARIANT_TOR && d.norm_rate > 0.f)   // hook on dense (EEGNet_tor.py:47-48)
-        TRY(launch_renorm_rows(params + d.oWd, (int64_t)d.M * d.NC, d.FEAT, d.FEAT, d.NC, d.pstride, d.norm_rate, st));
+    StageArgs a = {x, x_index, params, bn_state, mask1, mask2, out, nullptr, nullptr, workspace};
+    TRY(check_common(d, w, a, workspace_bytes, "eegnet_forward"));
+    EAV_REQUIRE(bn_state && out, EAV_ERR_BAD_ARG, "eegnet_forward: null pointer");
+    for (int s = 0; s < ST_FWD_END; ++s) TRY(run_stage(d, w, s, a, (cudaStream_t)stream));
     return 0;
 }
 
@@ -208,34 +305,10 @@ extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, co
                                    void *stream) {
     NetDims d;
     TRY(make_dims(cfg, &d));
-    EAV_REQUIRE(x && params && dout && grads && workspace, EAV_ERR_BAD_ARG, "eegnet_backward: null pointer");
     const WsLayout w = make_ws_layout(d);
-    EAV_REQUIRE(workspace_bytes >= w.total, EAV_ERR_WORKSPACE, "eegnet_backward: workspace %zu < required %zu", workspace_bytes, w.total);
-    EAV_REQUIRE(d.dropout_mode != EAV_DROPOUT_MASK || (mask1 && mask2), EAV_ERR_BAD_ARG, "eegnet_backward: dropout masks required");
-    cudaStream_t st = (cudaStream_t)stream;
-    float *part = WS(float, w.part);
-    float *partw = WS(float, w.partw);
-
-    TRY(launch_tail_bwd(d, dout, WS(float, w.probs), params, WS(float, w.y3), WS(float4, w.bnf3), mask2,
-                        WS(float, w.dz), WS(float, w.dz3), part, st));
-    TRY(launch_dense_bwd_w(d, WS(float, w.feat), WS(float, w.dz), grads, st));
-    TRY(launch_bn_bwd_finalize(d, 3, part, d.B, (double)d.B * d.T4, params, WS(float4, w.bnf3), WS(float4, w.bnb3), grads, st));
-    if (d.variant == EAV_VARIANT_TOR) {
-        TRY(launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), params,
-                                  WS(float, w.dd1), st));
-        TRY(launch_sepconv_bwd_dw(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
-                                  WS(float, w.d1), partw, grads, st));
-    } else {
-        TRY(launch_pw_bwd(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), WS(float, w.y3d),
-                          params, WS(float, w.dy3d), partw, grads, st));
-        TRY(launch_dwt_bwd(d, WS(float, w.dy3d), WS(float, w.d1), params, WS(float, w.dd1), partw, grads, st));
-    }
-    TRY(launch_pool1_bwd(d, WS(float, w.dd1), WS(float, w.y2), WS(float4, w.bnf2), mask1, WS(float, w.dz2), part, st));
-    TRY(launch_bn_bwd_finalize(d, 2, part, d.B, (double)d.B * d.T, params, WS(float4, w.bnf2), WS(float4, w.bnb2), grads, st));
-    TRY(launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
-                      WS(float4, w.bnf1), params, WS(float, w.dz1), partw, part, grads, st));
-    TRY(launch_bn_bwd_finalize(d, 1, part, d.B, (double)d.B * d.C * d.T, params, WS(float4, w.bnf1), WS(float4, w.bnb1), grads, st));
-    TRY(launch_tconv_bwd_dw(d, x, x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
-                            partw, grads, st));
+    StageArgs a = {x, x_index, const_cast<float *>(params), nullptr, mask1, mask2, nullptr, dout, grads, workspace};
+    TRY(check_common(d, w, a, workspace_bytes, "eegnet_backward"));
+    EAV_REQUIRE(dout && grads, EAV_ERR_BAD_ARG, "eegnet_backward: null pointer");
+    for (int s = ST_FWD_END; s < ST_COUNT; ++s) TRY(run_stage(d, w, s, a, (cudaStream_t)stream));
     return 0;
 }

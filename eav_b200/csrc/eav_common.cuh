@@ -8,6 +8,7 @@
 namespace eav {
 
 void set_error(const char *fmt, ...);
+void count_launch();   // bumps the process-wide kernel-launch counter (eav_launch_count)
 
 #define EAV_REQUIRE(cond, code, ...)            \
     do {                                        \
@@ -19,6 +20,7 @@ void set_error(const char *fmt, ...);
 
 #define EAV_CUDA_LAUNCH_CHECK(name)                                               \
     do {                                                                          \
+        ::eav::count_launch();                                                    \
         cudaError_t e__ = cudaGetLastError();                                     \
         if (e__ != cudaSuccess) {                                                 \
             ::eav::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
@@ -84,6 +86,7 @@ struct NetDims {
     int pad1l, pad2l;       // 'same' left paddings
     float p_drop, eps, momentum, norm_rate;
     uint64_t seed, step;
+    const unsigned long long *step_ptr;   // optional device-resident step counter
     int64_t pstride, bnstride;
     // parameter offsets (floats) inside one model's slice
     int64_t oW1, og1, ob1, oW2, og2, ob2, oW3, oW3p, og3, ob3, oWd, obd, n_params;

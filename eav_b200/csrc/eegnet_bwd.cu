@@ -19,11 +19,12 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
                 const float *__restrict__ params, int64_t pstride, int64_t oWd, const float *__restrict__ y3,
                 const float4 *__restrict__ bn3, const uint8_t *__restrict__ mask2, int B, int F2, int T4,
                 int T32, int P2, int NC, int softmax_out, int dropout_mode, float p_drop, uint64_t seed,
-                uint64_t step, float *__restrict__ dz, float *__restrict__ dz3, float *__restrict__ part) {
+                uint64_t step, const unsigned long long *__restrict__ step_ptr, float *__restrict__ dz, float *__restrict__ dz3, float *__restrict__ part) {
     extern __shared__ float sm[];  // dfeat_s[FEAT] + dz_s[NC]
     const int FEAT = F2 * T32;
     float *dfeat_s = sm, *dz_s = sm + FEAT;
     const int n = blockIdx.x, m = n / B, tid = threadIdx.x;
+    if (step_ptr) step = *step_ptr;
     if (tid == 0) {
         if (softmax_out) {
             float dot = 0.f;
@@ -82,7 +83,7 @@ int launch_tail_bwd(const NetDims &d, const float *dout, const float *probs, con
     size_t smem = (size_t)(d.FEAT + d.NC) * sizeof(float);
     tail_bwd_kernel<<<d.N, 128, smem, st>>>(dout, probs, params, d.pstride, d.oWd, y3, bn3, mask2, d.B, d.F2,
                                             d.T4, d.T32, d.P2, d.NC, d.variant == EAV_VARIANT_TOR,
-                                            d.dropout_mode, d.p_drop, d.seed, d.step, dz, dz3, part);
+                                            d.dropout_mode, d.p_drop, d.seed, d.step, d.step_ptr, dz, dz3, part);
     EAV_CUDA_LAUNCH_CHECK("tail_bwd");
     return 0;
 }
@@ -397,11 +398,12 @@ int launch_dwt_bwd(const NetDims &d, const float *dy3d, const float *d1, const f
 __global__ void __launch_bounds__(256)
 pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, const float4 *__restrict__ bnf2,
                  const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1, int dropout_mode,
-                 float p_drop, uint64_t seed, uint64_t step, int64_t rows, float *__restrict__ dz2,
+                 float p_drop, uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_ptr, int64_t rows, float *__restrict__ dz2,
                  float *__restrict__ part) {
     const int lane = threadIdx.x & 31;
     const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (step_ptr) step = *step_ptr;
     const int g = (int)(row % G), n = (int)(row / G);
     const float4 st = bnf2[(int64_t)(n / B) * G + g];
     const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
@@ -431,7 +433,7 @@ int launch_pool1_bwd(const NetDims &d, const float *dd1, const float *y2, const 
                      const uint8_t *mask1, float *dz2, float *part, cudaStream_t st) {
     int64_t rows = (int64_t)d.N * d.G;
     pool1_bwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(dd1, y2, bnf2, mask1, d.B, d.G, d.T, d.T4, d.P1,
-                                                               d.dropout_mode, d.p_drop, d.seed, d.step, rows,
+                                                               d.dropout_mode, d.p_drop, d.seed, d.step, d.step_ptr, rows,
                                                                dz2, part);
     EAV_CUDA_LAUNCH_CHECK("pool1_bwd");
     return 0;
@@ -717,7 +719,11 @@ static int launch_tconv_bwd_dw_rk(const NetDims &d, const float *x, const int32_
                                   cudaStream_t st, int cpm) {
     size_t smem = tconv_dw_smem<RK>(d.T);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: Samples=%d too large", d.T);
-    cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static bool attr_set = false;   // one flag per RK instantiation
+    if (!attr_set) {
+        cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
     tconv_bwd_dw_kernel<8, RK><<<d.M * cpm, TW_WARPS * 32, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train,
                                                                        d.B, d.C, d.T, d.K1, d.pad1l, cpm, part);
     return 0;

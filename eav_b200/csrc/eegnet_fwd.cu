@@ -280,8 +280,9 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
 // =================================================================================
 __global__ void pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
                                  const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1,
-                                 int dropout_mode, float p_drop, uint64_t seed, uint64_t step,
+                                 int dropout_mode, float p_drop, uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_ptr,
                                  int64_t total, float *__restrict__ d1) {
+    if (step_ptr) step = *step_ptr;
     const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -305,7 +306,7 @@ int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const
     int64_t total = (int64_t)d.N * d.G * d.T4;
     int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
     pool1_fwd_kernel<<<blocks, 256, 0, st>>>(y2, bn2, mask1, d.B, d.G, d.T, d.T4, d.P1, d.dropout_mode,
-                                             d.p_drop, d.seed, d.step, total, d1);
+                                             d.p_drop, d.seed, d.step, d.step_ptr, total, d1);
     EAV_CUDA_LAUNCH_CHECK("pool1_fwd");
     return 0;
 }
@@ -574,12 +575,13 @@ __global__ void __launch_bounds__(128)
 tail_fwd_kernel(const float *__restrict__ y3, const float4 *__restrict__ bn3,
                 const uint8_t *__restrict__ mask2, const float *__restrict__ params, int64_t pstride,
                 int64_t oWd, int64_t obd, int B, int F2, int T4, int T32, int P2, int NC, int softmax_out,
-                int dropout_mode, float p_drop, uint64_t seed, uint64_t step,
+                int dropout_mode, float p_drop, uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_ptr,
                 float *__restrict__ feat, float *__restrict__ out, float *__restrict__ probs_saved) {
     extern __shared__ float sm[];  // feat_s[FEAT] + z_s[NC]
     const int FEAT = F2 * T32;
     float *feat_s = sm, *z_s = sm + FEAT;
     const int n = blockIdx.x, m = n / B, tid = threadIdx.x;
+    if (step_ptr) step = *step_ptr;
     const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
     for (int i = tid; i < FEAT; i += blockDim.x) {
         int o = i / T32, v = i - o * T32;
@@ -630,7 +632,7 @@ int launch_tail_fwd(const NetDims &d, const float *y3, const float4 *bn3, const 
     EAV_REQUIRE(smem <= 48 * 1024, EAV_ERR_UNSUPPORTED, "tail_fwd: feature size %d too large", d.FEAT);
     tail_fwd_kernel<<<d.N, 128, smem, st>>>(y3, bn3, mask2, params, d.pstride, d.oWd, d.obd, d.B, d.F2, d.T4,
                                             d.T32, d.P2, d.NC, d.variant == EAV_VARIANT_TOR, d.dropout_mode,
-                                            d.p_drop, d.seed, d.step, feat, out, probs_saved);
+                                            d.p_drop, d.seed, d.step, d.step_ptr, feat, out, probs_saved);
     EAV_CUDA_LAUNCH_CHECK("tail_fwd");
     return 0;
 }

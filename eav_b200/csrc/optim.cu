@@ -25,6 +25,33 @@ __global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, 
     }
 }
 
+// Graph-replayable variant: t = *step_dev + 1 is read on the device and the bias
+// corrections are computed in-kernel (double, like torch's host arithmetic).
+__global__ void adam_graph_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                  float *__restrict__ v, int64_t n, const long long *__restrict__ step_dev,
+                                  float lr, float b1, float b2, float eps) {
+    __shared__ float sh[2];
+    if (threadIdx.x == 0) {
+        double t = (double)(*step_dev + 1);
+        double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
+        sh[0] = (float)((double)lr / bc1);
+        sh[1] = (float)sqrt(bc2);
+    }
+    __syncthreads();
+    const float step_size = sh[0], bc2_sqrt = sh[1];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i];
+        float mi = m[i], vi = v[i];
+        mi = mi + (gi - mi) * (1.f - b1);
+        vi = vi * b2 + (1.f - b2) * gi * gi;
+        float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+__global__ void counter_inc_kernel(long long *c) { *c += 1; }
+
 // torch.renorm(p=2, dim=0, maxnorm): rows with ||row||_2 > maxnorm are scaled by
 // maxnorm/(norm + 1e-7).  One warp per row.
 __global__ void renorm_rows_kernel(float *__restrict__ w, int64_t n_rows, int64_t row_len, int64_t row_stride,
@@ -132,6 +159,23 @@ extern "C" int eav_adam_step(float *params, const float *grads, float *exp_avg, 
     adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, step_size, bc2_sqrt,
                                                           beta1, beta2, eps);
     EAV_CUDA_LAUNCH_CHECK("adam_step");
+    return 0;
+}
+
+extern "C" int eav_adam_step_graph(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n,
+                                   int64_t *step_count_dev, float lr, float beta1, float beta2, float eps,
+                                   void *stream) {
+    EAV_REQUIRE(params && grads && exp_avg && exp_avg_sq && step_count_dev, EAV_ERR_BAD_ARG, "adam_step_graph: null pointer");
+    EAV_REQUIRE(n >= 0, EAV_ERR_BAD_ARG, "adam_step_graph: n=%lld", (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 0) {
+        int blocks = (int)std::min<int64_t>(cdiv64(n, 256), 148 * 8);
+        adam_graph_kernel<<<blocks, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n,
+                                                  reinterpret_cast<const long long *>(step_count_dev), lr, beta1, beta2, eps);
+        EAV_CUDA_LAUNCH_CHECK("adam_step_graph");
+    }
+    counter_inc_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long *>(step_count_dev));
+    EAV_CUDA_LAUNCH_CHECK("adam_step_graph(counter)");
     return 0;
 }
 

@@ -40,6 +40,8 @@ extern "C" {
 
 const char *eav_last_error_string(void);
 int eav_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process so far. */
+uint64_t eav_launch_count(void);
 /* 0 when the current device is compute capability 10.x, else EAV_ERR_UNSUPPORTED. */
 int eav_check_device(void);
 
@@ -118,6 +120,9 @@ typedef struct eav_eegnet_cfg {
     float   norm_rate;     /* max-norm of the forward hooks (variant 0); <= 0 disables */
     uint64_t seed;         /* Philox key (EAV_DROPOUT_PHILOX)                    */
     uint64_t step;         /* Philox stream position: change every step          */
+    uint64_t step_device_ptr; /* if non-zero: device address of an int64 step counter that
+                              replaces `step` (read at kernel run time, so a captured CUDA
+                              graph can be replayed with a fresh dropout stream)            */
 } eav_eegnet_cfg;
 
 /* Number of parameters of one model and the offsets (in floats) of its tensors inside
@@ -176,6 +181,21 @@ int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, const int32_t
                         size_t workspace_bytes, void *stream);
 
 /*
+ * Profiling hook: forward and backward are fixed sequences of named kernel stages
+ * (forward = [0, eav_eegnet_stage_forward_end()), backward = the rest).
+ * eav_eegnet_run_stage launches exactly ONE stage on the buffers a previous full
+ * forward/backward left in the workspace, so bench.py can time each kernel with CUDA
+ * events on the launching stream.  Same argument meaning as forward/backward.
+ */
+int eav_eegnet_stage_count(void);
+int eav_eegnet_stage_forward_end(void);
+const char *eav_eegnet_stage_name(int stage);
+int eav_eegnet_run_stage(const eav_eegnet_cfg *cfg, int stage, const float *x, const int32_t *x_index,
+                         float *params, float *bn_state, const uint8_t *mask1, const uint8_t *mask2,
+                         float *out, const float *dout, float *grads, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/*
  * torch.optim.Adam step (EEGNet_tor.py:82,110; betas/eps/no weight decay as there)
  * over a flat arena of n floats: m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g;
  * p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
@@ -184,6 +204,13 @@ int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, const int32_t
 int eav_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                   int64_t n, int64_t step_count, float lr, float beta1, float beta2,
                   float eps, void *stream);
+
+/* Same update with the step count t = *step_count_dev + 1 read on the device (bias
+ * corrections computed in-kernel), then *step_count_dev is incremented by a trailing
+ * 1-thread kernel: a captured CUDA graph of a whole training step replays correctly. */
+int eav_adam_step_graph(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                        int64_t n, int64_t *step_count_dev, float lr, float beta1, float beta2,
+                        float eps, void *stream);
 
 /* torch.renorm(p=2, dim=0, maxnorm) in place over `n_rows` rows of `row_len` floats
  * spaced `row_stride` apart (the max-norm hook body, EEGNet_tor.py:34,48). */

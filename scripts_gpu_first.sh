@@ -1,6 +1,6 @@
 #!/bin/bash
-# first GPU contact: run all gpu tests without -x and keep the log
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.txt 2>&1
-python -m pytest tests -m gpu -q --timeout=600 2>&1 | tail -80 > gpurun_out/pytest_gpu.log
-tail -60 gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -q --timeout=900 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
+tail -40 gpurun_out/pytest_gpu.log
+python __graft_entry__.py smoke 2>&1 | tail -5
+python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json

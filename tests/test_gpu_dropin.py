@@ -1,0 +1,138 @@
+"""-m gpu tests of the drop-in classes (the reference's own Python surface) end to end."""
+import contextlib
+import io
+import re
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _load_init(model, g):
+    model.load_state_dict({k[6:]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith("init::")})
+
+
+def test_eegnet_tor_module_autograd_matches_reference(golden):
+    """Unmodified user code: criterion(model(x), y).backward() runs on the kernels."""
+    import gpu_util as U
+    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
+    g = golden("eegnet_tor_b8.npz")
+    model = EEGNet_tor(5)
+    _load_init(model, g)
+    model = model.cuda()
+    model.dropout_source = "torch_cpu"
+    x, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    crit = torch.nn.CrossEntropyLoss()
+    for mode in ("train", "eval"):
+        _load_init(model, g)
+        model.train(mode == "train")
+        model.zero_grad()
+        torch.manual_seed(100)
+        p = model(x)
+        loss = crit(p, y)
+        loss.backward()
+        assert p.shape == (8, 5)
+        assert U.rel_max(p.detach().cpu().numpy(), g[f"{mode}::probs"]) < TOL
+        assert abs(loss.item() - float(g[f"{mode}::loss"])) < TOL * float(g[f"{mode}::loss"])
+        for k, prm in model.named_parameters():
+            assert U.rel_l2(prm.grad.cpu().numpy(), g[f"{mode}::grad::{k}"]) < TOL, (mode, k)
+        sd = model.state_dict()
+        for k in g.files:
+            if k.startswith(f"{mode}::after::"):
+                name = k.split("::")[-1]
+                assert np.allclose(sd[name].cpu().numpy(), g[k], rtol=1e-5, atol=1e-6), name
+    # 3-D input is accepted (superset); torch optimizers update the arena in place
+    model.eval()
+    with torch.no_grad():
+        p3 = model(x[:, 0])
+        p4 = model(x)
+    assert torch.equal(p3, p4)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    before = model._arena.clone()
+    model.zero_grad(); crit(model(x), y).backward(); opt.step()
+    assert model._arena_ok() and not torch.equal(before, model._arena)
+
+
+def test_trainer_uni_loop_matches_reference(golden):
+    import golden_inputs as GI
+    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor, Trainer_uni
+    g = golden("trainer_uni_3ep.npz")
+    data = GI.trainer_inputs()
+    model = EEGNet_tor(5)
+    _load_init(model, g)
+    model.dropout_source = "torch_cpu"
+    trainer = Trainer_uni(model, list(data), lr=1e-3, batch_size=16, num_epochs=3)
+    trainer.record_losses = True
+    torch.manual_seed(77)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        trainer.train()
+    got = torch.stack(trainer.loss_history).cpu().numpy()
+    ref = g["train_step_loss"]
+    assert got.shape == ref.shape == (9,)
+    assert np.abs(got - ref).max() < TOL * np.abs(ref).max(), (got, ref)
+    # same print cadence / format as the reference, values equal to print precision
+    ref_lines = str(g["stdout"]).strip().splitlines()
+    got_lines = buf.getvalue().strip().splitlines()
+    assert len(ref_lines) == len(got_lines) == 6
+    for a, b in zip(got_lines, ref_lines):
+        assert a.split("Loss")[0] == b.split("Loss")[0]
+        va = [float(t) for t in re.findall(r"\d+\.\d+", a)]
+        vb = [float(t) for t in re.findall(r"\d+\.\d+", b)]
+        assert len(va) == len(vb) and np.allclose(va, vb, atol=2e-4), (a, b)
+    assert int(model.firstBN.num_batches_tracked) == 3                # F5: BN trains only in epoch 1
+    assert not model.training
+    final = model.state_dict()
+    for k in ("firstBN.running_mean", "separableBN.running_var"):
+        assert np.allclose(final[k].cpu().numpy(), g[f"final::{k}"], rtol=1e-4, atol=1e-6), k
+
+
+def test_dataload_eeg_dropin_vs_oracle():
+    import eeg_oracle as O
+    from eav_b200.Dataload_eeg import DataLoadEEG
+    from eav_b200.EAV_datasplit import EAVDataSplit
+    raw, label = O.synth_subject(3)
+    d = DataLoadEEG(subject=3, band=[5, 30])
+    d.set_raw(np.transpose(raw, (2, 1, 0)), label)          # (Time, Channels, Trials) like the .mat
+    x_dev, y = d.prepare_data_device()
+    xo, yo = O.prepare_data(raw, label, [5, 30])
+    assert np.array_equal(y, yo) and x_dev.shape == (400, 30, 500)
+    x = x_dev.cpu().numpy()
+    rms = np.sqrt((xo ** 2).mean(axis=(0, 2)))
+    assert (np.abs(x - xo).max(axis=(0, 2)) / rms).max() < 1e-5
+    # shipped labels {1,3,5,7,9} through the shipped split -> 112/48; remap -> 280/120
+    trx, try_, tex, tey = EAVDataSplit(x, y).get_split(h_idx=56)
+    assert trx.shape == (112, 30, 500) and tex.shape == (48, 30, 500)
+    trx, try_, tex, tey = EAVDataSplit(x, (y - 1) // 2).get_split(h_idx=56)
+    assert trx.shape == (280, 30, 500) and tex.shape == (120, 30, 500)
+    # staged API leaves the same attributes and agrees with the fused path
+    d2 = DataLoadEEG(subject=3, band=[5, 30])
+    d2.set_raw(np.transpose(raw, (2, 1, 0)), label)
+    d2.downsampling()
+    assert d2.seg.shape == (30, 2000, 200)
+    d2.bandpass_filter()
+    assert d2.seg_f.shape == (30, 2000, 200)
+    d2.segment_and_select_classes()
+    assert d2.seg_f_div.shape == (400, 30, 500) and np.array_equal(d2.label_div, y)
+    assert (np.abs(d2.seg_f_div - xo).max(axis=(0, 2)) / rms).max() < 1e-5
+
+
+def test_cnn_eeg_trainer_runs_and_learns():
+    from torch.utils.data import TensorDataset
+    from eav_b200.CNN_torch.CNN_EEG import EEGNet, EEGNetTrainer
+    torch.manual_seed(0)
+    X = torch.randn(96, 64, 128)
+    y = (X[:, :8, :32].mean(dim=(1, 2)) > 0).long() + 2 * (X[:, 8:16, :32].mean(dim=(1, 2)) > 0).long()
+    model = EEGNet(nb_classes=4, Chans=64, Samples=128, dropoutRate=0.25)
+    with contextlib.redirect_stdout(io.StringIO()):
+        tr = EEGNetTrainer(model, TensorDataset(X[:80], y[:80]), TensorDataset(X[80:], y[80:]), batch_size=16, epochs=3, lr=1e-2)
+        first = tr.train_epoch()
+        for _ in range(12):
+            last = tr.train_epoch()
+        vloss, acc = tr.validate_epoch()
+    assert last < first and np.isfinite(vloss) and 0 <= acc <= 100
+    preds = tr.predict()
+    assert len(preds) == 16 and all(isinstance(p, int) for p in preds)
