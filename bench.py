@@ -41,7 +41,7 @@ PREPROC_BYTES_PER_SUBJECT = 264e6  # 240 MB raw f32 read once + 24 MB
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--subjects", type=int, default=N_SUBJECTS, help="subject models per GPU")
