@@ -95,13 +95,11 @@ WsLayout make_ws_layout(const NetDims &d) {
     pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
     pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
     w.part = take(pa);
-    // weight-gradient partials (largest user)
-    size_t pb = 0;
-    pb = max_sz(pb, N * d.G * d.C);                                       // dw_bwd
-    pb = max_sz(pb, (size_t)d.M * tconv_dw_ctas_per_model(d) * d.F1 * d.K1);  // tconv_bwd_dw
-    if (d.variant == EAV_VARIANT_TOR) pb = max_sz(pb, (size_t)d.M * sepconv_dw_splits(d) * d.F2 * d.G * 16);
-    else pb = max_sz(pb, max_sz(N * d.F2 * d.G, N * d.G * d.K2));
-    w.partw = take(pb);
+    // weight-gradient partials, one region per layer (the block-2 kernels run on a forked stream)
+    w.partw = take((size_t)d.M * tconv_dw_ctas_per_model(d) * d.F1 * d.K1);        // tconv_bwd_dw
+    w.partw2 = take(N * d.G * d.C);                                                // dw_bwd
+    if (d.variant == EAV_VARIANT_TOR) w.partw3 = take((size_t)d.M * sepconv_dw_splits(d) * d.F2 * d.G * 16);
+    else w.partw3 = take(max_sz(N * d.F2 * d.G, N * d.G * d.K2));
     w.dz3 = take(N * d.F2 * d.T4);
     w.dd1 = take(N * d.G * d.T4);
     w.dy3d = take(d.variant == EAV_VARIANT_CNN ? N * d.G * d.T4 : 0);
@@ -198,11 +196,11 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     void *workspace = a.workspace;
     float *part = WS(float, w.part);
     float *pstat = d.bn_train ? part : nullptr;
-    float *partw = WS(float, w.partw);
+    float *partw = WS(float, w.partw), *partw2 = WS(float, w.partw2), *partw3 = WS(float, w.partw3);
     const bool tor = d.variant == EAV_VARIANT_TOR;
     // rows of BatchNorm partial sums each producer writes per model
     const int rows1 = d.B * cdiv(d.C, 4) * cdiv(d.T, 512);
-    const int rows2 = d.B * cdiv(d.T, 128);
+    const int rows2 = d.B * dw_fwd_tiles(d);
     const int rows3 = tor ? cdiv(d.B, 2) * cdiv(d.T4, 128) : d.B;
     switch (stage) {
         case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.y1), pstat, nullptr, st);
@@ -236,19 +234,19 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
                 return launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
                                              a.params, WS(float, w.dd1), st);
             return launch_pw_bwd(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), WS(float, w.y3d),
-                                 a.params, WS(float, w.dy3d), partw, a.grads, st);
+                                 a.params, WS(float, w.dy3d), partw3, a.grads, st);
         case ST_SEPCONV_BWD_DW:
             if (tor)
                 return launch_sepconv_bwd_dw(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
-                                             WS(float, w.d1), partw, a.grads, st);
-            return launch_dwt_bwd(d, WS(float, w.dy3d), WS(float, w.d1), a.params, WS(float, w.dd1), partw, a.grads, st);
+                                             WS(float, w.d1), partw3, a.grads, st);
+            return launch_dwt_bwd(d, WS(float, w.dy3d), WS(float, w.d1), a.params, WS(float, w.dd1), partw3, a.grads, st);
         case ST_POOL1_BWD:
             return launch_pool1_bwd(d, WS(float, w.dd1), WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.dz2), part, st);
         case ST_BN2_BWD:
             return launch_bn_bwd_finalize(d, 2, part, d.B, (double)d.B * d.T, a.params, WS(float4, w.bnf2), WS(float4, w.bnb2), a.grads, st);
         case ST_DW_BWD:
             return launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
-                                 WS(float4, w.bnf1), a.params, WS(float, w.dz1), partw, part, a.grads, st);
+                                 WS(float4, w.bnf1), a.params, WS(float, w.dz1), partw2, part, a.grads, st);
         case ST_BN1_BWD:
             return launch_bn_bwd_finalize(d, 1, part, d.B, (double)d.B * d.C * d.T, a.params, WS(float4, w.bnf1), WS(float4, w.bnb1), a.grads, st);
         case ST_TCONV_BWD_DW:
@@ -258,6 +256,22 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     }
     set_error("run_stage: unknown stage %d", stage);
     return EAV_ERR_BAD_ARG;
+}
+
+// One helper stream + two events per device, created on first use and kept for the process.
+struct SideStream { cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream *side_stream() {
+    static SideStream pool[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!made[dev]) {
+        if (cudaStreamCreateWithFlags(&pool[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        cudaEventCreateWithFlags(&pool[dev].fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&pool[dev].join, cudaEventDisableTiming);
+        made[dev] = true;
+    }
+    return &pool[dev];
 }
 
 static int check_common(const NetDims &d, const WsLayout &w, const StageArgs &a, size_t workspace_bytes, const char *who) {
@@ -309,6 +323,23 @@ extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, co
     StageArgs a = {x, x_index, const_cast<float *>(params), nullptr, mask1, mask2, nullptr, dout, grads, workspace};
     TRY(check_common(d, w, a, workspace_bytes, "eegnet_backward"));
     EAV_REQUIRE(dout && grads, EAV_ERR_BAD_ARG, "eegnet_backward: null pointer");
-    for (int s = ST_FWD_END; s < ST_COUNT; ++s) TRY(run_stage(d, w, s, a, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    // The weight gradients of the dense layer and of the block-2 conv do not feed the rest of
+    // the chain: they run on a forked stream (works under stream capture too) and fill the SM
+    // time the latency/HBM-bound kernels of the main chain leave idle.  Joined before return.
+    SideStream *side = (d.variant == EAV_VARIANT_TOR) ? side_stream() : nullptr;
+    for (int s = ST_FWD_END; s < ST_COUNT; ++s) {
+        if (side != nullptr && (s == ST_DENSE_BWD_W || s == ST_SEPCONV_BWD_DW)) continue;   // issued on the fork
+        TRY(run_stage(d, w, s, a, st));
+        if (side != nullptr && (s == ST_TAIL_BWD || s == ST_BN3_BWD)) {
+            cudaEventRecord(side->fork, st);
+            cudaStreamWaitEvent(side->stream, side->fork, 0);
+            TRY(run_stage(d, w, s == ST_TAIL_BWD ? ST_DENSE_BWD_W : ST_SEPCONV_BWD_DW, a, side->stream));
+        }
+    }
+    if (side != nullptr) {
+        cudaEventRecord(side->join, side->stream);
+        cudaStreamWaitEvent(st, side->join, 0);
+    }
     return 0;
 }

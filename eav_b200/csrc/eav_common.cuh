@@ -104,7 +104,9 @@ struct WsLayout {
     size_t y1, y2, d1, y3d, y3, feat, probs, dz;      // saved activations
     size_t bnf1, bnf2, bnf3, bnb1, bnb2, bnb3;         // float4 per (m, ch)
     size_t part;                                       // BatchNorm partial sums
-    size_t partw;                                      // weight-gradient partials
+    size_t partw;                                      // weight-gradient partials: temporal conv (dW1)
+    size_t partw2, partw3;                             // ... depthwise (dW2), block-2 conv (dW3): separate so the
+                                                       // dW3 kernels can run on a forked stream
     size_t dz3, dd1, dy3d, dz2, dz1;                   // backward scratch
     size_t total;
 };

@@ -409,20 +409,38 @@ pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, co
     const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
     const float sc = inv_keep / (float)P1;
     float s1 = 0.f, s2 = 0.f;
-    for (int t = lane; t < T; t += 32) {
-        int u = t / P1;
-        float y = y2[row * T + t];
-        float gval = 0.f;
-        if (u < T4) {
-            int64_t e = row * T4 + u;
-            bool keep = true;
-            if (dropout_mode == EAV_DROPOUT_MASK) keep = mask1[e] != 0;
-            else if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep(seed, step, 1u, (uint64_t)e, p_drop);
-            if (keep) gval = dd1[e] * sc * elu_grad_from_pre(fmaf(y, st.z, st.w));
+    auto upstream = [&](int u) -> float {       // d(loss)/d(pooled activation) after dropout, per input sample
+        if (u >= T4) return 0.f;
+        const int64_t e = row * T4 + u;
+        bool keep = true;
+        if (dropout_mode == EAV_DROPOUT_MASK) keep = mask1[e] != 0;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep(seed, step, 1u, (uint64_t)e, p_drop);
+        return keep ? dd1[e] * sc : 0.f;
+    };
+    if (P1 == 4 && (T & 3) == 0) {              // one pooling window == one aligned float4
+        for (int u = lane; 4 * u < T; u += 32) {
+            const float up = upstream(u);
+            const float4 y = *reinterpret_cast<const float4 *>(y2 + row * T + 4 * u);
+            float4 o;
+            o.x = up * elu_grad_from_pre(fmaf(y.x, st.z, st.w));
+            o.y = up * elu_grad_from_pre(fmaf(y.y, st.z, st.w));
+            o.z = up * elu_grad_from_pre(fmaf(y.z, st.z, st.w));
+            o.w = up * elu_grad_from_pre(fmaf(y.w, st.z, st.w));
+            *reinterpret_cast<float4 *>(dz2 + row * T + 4 * u) = o;
+            s1 += (o.x + o.y) + (o.z + o.w);
+            s2 = fmaf(o.x, (y.x - st.x) * st.y, s2);
+            s2 = fmaf(o.y, (y.y - st.x) * st.y, s2);
+            s2 = fmaf(o.z, (y.z - st.x) * st.y, s2);
+            s2 = fmaf(o.w, (y.w - st.x) * st.y, s2);
         }
-        dz2[row * T + t] = gval;
-        s1 += gval;
-        s2 = fmaf(gval, (y - st.x) * st.y, s2);
+    } else {
+        for (int t = lane; t < T; t += 32) {
+            const float y = y2[row * T + t];
+            const float gval = upstream(t / P1) * elu_grad_from_pre(fmaf(y, st.z, st.w));
+            dz2[row * T + t] = gval;
+            s1 += gval;
+            s2 = fmaf(gval, (y - st.x) * st.y, s2);
+        }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
@@ -448,6 +466,17 @@ int launch_pool1_bwd(const NetDims &d, const float *dd1, const float *y2, const 
 constexpr int DB_THREADS = 256;
 constexpr int DB_TS = 16;   // t-slices for the dW2 reduction
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// smem layout (floats): y1s [C][TSa] | dys [8][TSa] | w2s [8][C] | red [max(DB_TS*D*C, 8*TSa)];  TSa = roundup4(T) + 4
+// The raw conv output y1, dz2 (and y2 in train mode, parked in `red`) are staged with 16-byte
+// cp.async (LDGSTS): every load of the CTA is in flight at once and no register is tied up.
+// a1 = act(BN1(y1)) and act' are recomputed from the staged y1, so y1 is read from HBM once.
 __global__ void __launch_bounds__(DB_THREADS, 2)
 dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const float4 *__restrict__ bnf2,
               const float4 *__restrict__ bnb2, const float *__restrict__ y1, const float4 *__restrict__ bnf1,
@@ -455,47 +484,64 @@ dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const
               int F1, int D, int C, int T, float *__restrict__ dz1, float *__restrict__ part_w,
               float *__restrict__ part_bn) {
     extern __shared__ __align__(16) float smem[];
-    const int TS = T + 1;                 // a1 row stride (odd-ish => conflict-free column walks)
-    float *a1s = smem;                    // [C][TS]
-    float *dys = a1s + ((C * TS + 3) & ~3);  // [T][DMAXB=8]
-    float *w2s = dys + T * 8;             // [D][C]
-    float *red = w2s + 8 * C;             // [DB_TS][D*C] for the dW2 cross-slice reduction (reuses after phase 1)
+    const int TSa = ((T + 3) & ~3) + 4;
+    float *y1s = smem;                    // [C][TSa]   raw conv output, zero padded past T
+    float *dys = y1s + C * TSa;           // [8][TSa]   dL/d(depthwise output) (BN2 backward applied), rows >= D zero
+    float *w2s = dys + 8 * TSa;           // [8][C]
+    float *red = w2s + 8 * C;             // [DB_TS][D*C]  (first holds the staged y2 rows in train mode)
     const int n = blockIdx.x / F1, f = blockIdx.x - n * F1, m = n / B;
-    const int G = F1 * D, tid = threadIdx.x;
+    const int G = F1 * D, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = DB_THREADS / 32;
     const float4 s1 = bnf1[(int64_t)m * F1 + f];
+    const bool vec = (T & 3) == 0;
+    const float *y1r = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T;
 
-    // stage dy2 (BN2 backward applied) as [t][d], W2 slice, and a1
-    for (int i = tid; i < D * T; i += DB_THREADS) {
-        int dd = i / T, t = i - dd * T;
-        int g = f * D + dd;
-        int64_t idx = ((int64_t)n * G + g) * T + t;
-        float v = dz2[idx];
-        const float4 kb = bnb2[(int64_t)m * G + g];
-        if (bn_train) {
-            const float4 kf = bnf2[(int64_t)m * G + g];
-            v = kb.x * (v - kb.y - (y2[idx] - kf.x) * kf.y * kb.z);
+    // ---- staging: one warp per row, lanes along time
+    for (int r = warp; r < C + 16; r += NW) {
+        const float *src;
+        float *dst;
+        if (r < C) { src = y1r + (int64_t)r * T; dst = y1s + r * TSa; }
+        else if (r < C + 8) {
+            const int dd = r - C;
+            dst = dys + dd * TSa;
+            src = (dd < D) ? dz2 + ((int64_t)n * G + f * D + dd) * T : nullptr;
         } else {
-            v = kb.x * v;
+            const int dd = r - C - 8;
+            dst = red + dd * TSa;
+            src = (bn_train && dd < D) ? y2 + ((int64_t)n * G + f * D + dd) * T : nullptr;
+            if (src == nullptr) continue;
         }
-        dys[t * 8 + dd] = v;
+        if (src == nullptr) {
+            for (int t = lane; t < TSa; t += 32) dst[t] = 0.f;
+            continue;
+        }
+        if (vec) for (int t = 4 * lane; t < T; t += 128) cp_async16(dst + t, src + t);
+        else for (int t = lane; t < T; t += 32) dst[t] = src[t];
+        for (int t = T + lane; t < TSa; t += 32) dst[t] = 0.f;
     }
-    if (D < 8)
-        for (int i = tid; i < T * 8; i += DB_THREADS)
-            if ((i & 7) >= D) dys[i] = 0.f;
     const float *W2 = params + (int64_t)m * pstride + oW2 + (int64_t)f * D * C;
     for (int i = tid; i < 8 * C; i += DB_THREADS) w2s[i] = (i < D * C) ? W2[i] : 0.f;
-    const float *y1r = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T;
-    for (int i = tid; i < C * T; i += DB_THREADS) {
-        int c = i / T, t = i - c * T;
-        float v = fmaf(y1r[i], s1.z, s1.w);
-        a1s[c * TS + t] = elu1 ? elu_f(v) : v;
+    cp_async_wait_all();
+    __syncthreads();
+    // BatchNorm-2 backward in place on the staged rows: dy2 = k (dz2 - c1 - xhat2 c2)
+    for (int dd = warp; dd < D; dd += NW) {
+        const float4 kb = bnb2[(int64_t)m * G + f * D + dd];
+        const float4 kf = bnf2[(int64_t)m * G + f * D + dd];
+        float *row = dys + dd * TSa;
+        const float *yrow = red + dd * TSa;
+        for (int t = lane; t < T; t += 32) {
+            float v = row[t];
+            if (bn_train) v = kb.x * (v - kb.y - (yrow[t] - kf.x) * kf.y * kb.z);
+            else v = kb.x * v;
+            row[t] = v;
+        }
     }
     __syncthreads();
 
-    // phase 1: dW2 partial.  work item = (channel pair cp, t-slice ts); 16 accumulators.
+    // ---- phase 1: dW2 partial.  work item = (channel pair, t-slice); four time steps per smem load.
     {
         const int n_cp = (C + 1) / 2;
-        const int per = ((T + DB_TS - 1) / DB_TS) | 1;   // odd: slices start in different banks
+        const int per = ((((T + 3) >> 2) + DB_TS - 1) / DB_TS) << 2;      // slice length, multiple of 4
         for (int item = tid; item < n_cp * DB_TS; item += DB_THREADS) {
             const int cp = item % n_cp, ts = item / n_cp;
             float acc[2][8];
@@ -504,19 +550,26 @@ dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const
 #pragma unroll
                 for (int dd = 0; dd < 8; ++dd) acc[q][dd] = 0.f;
             const int c0 = 2 * cp, c1 = (2 * cp + 1 < C) ? 2 * cp + 1 : c0;
-            const int t_lo = min(T, ts * per), t_hi = min(T, t_lo + per);
-            for (int t = t_lo; t < t_hi; ++t) {
-                float4 da = *reinterpret_cast<const float4 *>(dys + t * 8);
-                float4 db = *reinterpret_cast<const float4 *>(dys + t * 8 + 4);
-                const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-                float a0 = a1s[c0 * TS + t], a1v = a1s[c1 * TS + t];
+            const int t_lo = min(TSa - 4, ts * per), t_hi = min(TSa - 4, t_lo + per);
+            for (int t = t_lo; t < t_hi; t += 4) {
+                float4 a0 = *reinterpret_cast<const float4 *>(y1s + c0 * TSa + t);
+                float4 a1v = *reinterpret_cast<const float4 *>(y1s + c1 * TSa + t);
+                // a = act(BN1(y1)); the zero pads past T meet zero dy2, so their value is irrelevant
+                a0.x = fmaf(a0.x, s1.z, s1.w); a0.y = fmaf(a0.y, s1.z, s1.w); a0.z = fmaf(a0.z, s1.z, s1.w); a0.w = fmaf(a0.w, s1.z, s1.w);
+                a1v.x = fmaf(a1v.x, s1.z, s1.w); a1v.y = fmaf(a1v.y, s1.z, s1.w); a1v.z = fmaf(a1v.z, s1.z, s1.w); a1v.w = fmaf(a1v.w, s1.z, s1.w);
+                if (elu1) {
+                    a0.x = elu_f(a0.x); a0.y = elu_f(a0.y); a0.z = elu_f(a0.z); a0.w = elu_f(a0.w);
+                    a1v.x = elu_f(a1v.x); a1v.y = elu_f(a1v.y); a1v.z = elu_f(a1v.z); a1v.w = elu_f(a1v.w);
+                }
 #pragma unroll
                 for (int dd = 0; dd < 8; ++dd) {
-                    acc[0][dd] = fmaf(dv[dd], a0, acc[0][dd]);
-                    acc[1][dd] = fmaf(dv[dd], a1v, acc[1][dd]);
+                    const float4 dv = *reinterpret_cast<const float4 *>(dys + dd * TSa + t);
+                    acc[0][dd] = fmaf(dv.x, a0.x, fmaf(dv.y, a0.y, fmaf(dv.z, a0.z, fmaf(dv.w, a0.w, acc[0][dd]))));
+                    acc[1][dd] = fmaf(dv.x, a1v.x, fmaf(dv.y, a1v.y, fmaf(dv.z, a1v.z, fmaf(dv.w, a1v.w, acc[1][dd]))));
                 }
             }
-            // red[ts][dd][c]
+            // `red` still holds the staged y2 rows until every thread is past the transform above
+            // (guaranteed by the __syncthreads), so it can be overwritten now.
 #pragma unroll
             for (int dd = 0; dd < 8; ++dd) {
                 if (dd < D) {
@@ -534,29 +587,59 @@ dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const
         }
     }
 
-    // phase 2: dz1 and BN1 partials.  thread per t.
+    // ---- phase 2: dz1 = act'(.) * (W2new^T dy2) and BN1 partial sums.
     float p1 = 0.f, p2 = 0.f;
-    for (int t = tid; t < T; t += DB_THREADS) {
-        float4 da = *reinterpret_cast<const float4 *>(dys + t * 8);
-        float4 db = *reinterpret_cast<const float4 *>(dys + t * 8 + 4);
-        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-        for (int c = 0; c < C; ++c) {
-            float s = 0.f;
+    if (vec) {
+        // thread = (group of 4 time steps, channel range): all 256 threads busy for T = 500
+        const int n_t4 = T >> 2;
+        const int n_cr = max(1, DB_THREADS / n_t4);            // channel ranges processed concurrently
+        const int c_per = (C + n_cr - 1) / n_cr;
+        for (int item = tid; item < n_t4 * n_cr; item += DB_THREADS) {
+            const int t = (item % n_t4) * 4, cr = item / n_t4;
+            float4 dv[8];
 #pragma unroll
-            for (int dd = 0; dd < 8; ++dd) s = fmaf(w2s[dd * C + c], dv[dd], s);   // rows >= D are zero
-            float a = a1s[c * TS + t];
-            float gr = elu1 ? (a > 0.f ? 1.f : a + 1.f) : 1.f;
-            float g = s * gr;
-            int64_t idx = (int64_t)c * T + t;
-            dz1[(((int64_t)n * F1 + f) * C) * (int64_t)T + idx] = g;
-            p1 += g;
-            p2 = fmaf(g, (y1r[idx] - s1.x) * s1.y, p2);
+            for (int dd = 0; dd < 8; ++dd) dv[dd] = *reinterpret_cast<const float4 *>(dys + dd * TSa + t);
+            const int c_hi = min(C, (cr + 1) * c_per);
+            for (int c = cr * c_per; c < c_hi; ++c) {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) {           // rows >= D of w2s are zero
+                    const float w = w2s[dd * C + c];
+                    s.x = fmaf(w, dv[dd].x, s.x); s.y = fmaf(w, dv[dd].y, s.y);
+                    s.z = fmaf(w, dv[dd].z, s.z); s.w = fmaf(w, dv[dd].w, s.w);
+                }
+                const float4 y = *reinterpret_cast<const float4 *>(y1s + c * TSa + t);
+                if (elu1) {
+                    s.x *= elu_grad_from_pre(fmaf(y.x, s1.z, s1.w)); s.y *= elu_grad_from_pre(fmaf(y.y, s1.z, s1.w));
+                    s.z *= elu_grad_from_pre(fmaf(y.z, s1.z, s1.w)); s.w *= elu_grad_from_pre(fmaf(y.w, s1.z, s1.w));
+                }
+                *reinterpret_cast<float4 *>(dz1 + (((int64_t)n * F1 + f) * C + c) * (int64_t)T + t) = s;
+                p1 += (s.x + s.y) + (s.z + s.w);
+                p2 = fmaf(s.x, (y.x - s1.x) * s1.y, p2); p2 = fmaf(s.y, (y.y - s1.x) * s1.y, p2);
+                p2 = fmaf(s.z, (y.z - s1.x) * s1.y, p2); p2 = fmaf(s.w, (y.w - s1.x) * s1.y, p2);
+            }
+        }
+    } else {
+        for (int t = tid; t < T; t += DB_THREADS) {
+            float dv[8];
+#pragma unroll
+            for (int dd = 0; dd < 8; ++dd) dv[dd] = dys[dd * TSa + t];
+            for (int c = 0; c < C; ++c) {
+                float s = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < 8; ++dd) s = fmaf(w2s[dd * C + c], dv[dd], s);
+                const float y = y1s[c * TSa + t];
+                const float g = s * (elu1 ? elu_grad_from_pre(fmaf(y, s1.z, s1.w)) : 1.f);
+                dz1[(((int64_t)n * F1 + f) * C + c) * (int64_t)T + t] = g;
+                p1 += g;
+                p2 = fmaf(g, (y - s1.x) * s1.y, p2);
+            }
         }
     }
     __shared__ float redb[DB_THREADS / 32][2];
     p1 = warp_sum(p1);
     p2 = warp_sum(p2);
-    if ((tid & 31) == 0) { redb[tid >> 5][0] = p1; redb[tid >> 5][1] = p2; }
+    if (lane == 0) { redb[warp][0] = p1; redb[warp][1] = p2; }
     __syncthreads();
     if (tid < 2) {
         float s = 0.f;
@@ -570,8 +653,10 @@ int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const flo
                   const float4 *bnb2, const float *y1, const float4 *bnf1, const float *params,
                   float *dz1, float *part_w, float *part_bn, float *grads, cudaStream_t st) {
     EAV_REQUIRE(d.D <= 8, EAV_ERR_UNSUPPORTED, "dw_bwd: D=%d > 8 unsupported", d.D);
-    const int TS = d.T + 1;
-    size_t fl = (size_t)((d.C * TS + 3) & ~3) + (size_t)d.T * 8 + 8 * d.C + (size_t)DB_TS * d.D * d.C;
+    const int TSa = ((d.T + 3) & ~3) + 4;
+    size_t redn = (size_t)DB_TS * d.D * d.C;
+    if (redn < (size_t)8 * TSa) redn = (size_t)8 * TSa;
+    size_t fl = (size_t)d.C * TSa + (size_t)8 * TSa + 8 * d.C + redn;
     size_t smem = fl * sizeof(float);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "dw_bwd: Chans*Samples too large for one CTA");
     static bool attr_set = false;
@@ -609,7 +694,7 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
     const int XS = (Tp + 32 * RK + 8 + 3) & ~3;      // x row incl. both paddings
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *xs = smem + warp * (XS + TW_TCH * F1);    // per-warp private staging
-    float *dys = xs + XS;                            // [TW_TCH][F1]
+    float *dys = xs + XS;                            // [F1][TW_TCH]
     const int m = blockIdx.x / ctas_per_model, j = blockIdx.x - m * ctas_per_model;
     const int rows = B * C;                          // rows of this model
     const int r_lo = (int)((int64_t)rows * j / ctas_per_model), r_hi = (int)((int64_t)rows * (j + 1) / ctas_per_model);
@@ -620,33 +705,76 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
 #pragma unroll
         for (int q = 0; q < RK; ++q) acc[f][q] = 0.f;
 
+    const bool vec_ok = (T & 3) == 0;
     for (int r = r_lo + warp; r < r_hi; r += TW_WARPS) {
         const int b = r / C, c = r - b * C;
         const int64_t n = (int64_t)m * B + b;
         const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
         __syncwarp();
-        // xs[i] = x[i - padl], zero padded
+        // xs[i] = x[i - padl], zero padded on both sides
         const float *xsrc = x + (xrow * C + c) * (int64_t)T;
-        for (int i = lane; i < XS; i += 32) {
-            int t = i - padl;
-            xs[i] = (t >= 0 && t < T) ? xsrc[t] : 0.f;
+        if (vec_ok) {
+            for (int i = lane; i < padl; i += 32) xs[i] = 0.f;
+            for (int i = padl + T + lane; i < XS; i += 32) xs[i] = 0.f;
+#pragma unroll 4
+            for (int t = 4 * lane; t < T; t += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(xsrc + t);
+                float *d = xs + padl + t;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = lane; i < XS; i += 32) {
+                int t = i - padl;
+                xs[i] = (t >= 0 && t < T) ? xsrc[t] : 0.f;
+            }
         }
         for (int tc = 0; tc < Tp; tc += TW_TCH) {
             const int tn = min(TW_TCH, Tp - tc);     // multiple of 4
             __syncwarp();
+            // dys[f][t] = dL/d(conv output): BatchNorm-1 backward applied while staging.
+            if (vec_ok) {
+                const int t = 4 * lane;
+                const bool act = t < tn;              // T % 4 == 0: the whole float4 is in range
 #pragma unroll
-            for (int f = 0; f < F1; ++f) {
-                const float4 kb = bnb1[(int64_t)m * F1 + f];
-                const float4 kf = bnf1[(int64_t)m * F1 + f];
-                const int64_t base = ((n * F1 + f) * C + c) * (int64_t)T + tc;
-                for (int t = lane; t < tn; t += 32) {
-                    float v = 0.f;
-                    if (tc + t < T) {
-                        v = dz1[base + t];
-                        if (bn_train) v = kb.x * (v - kb.y - (y1[base + t] - kf.x) * kf.y * kb.z);
-                        else v = kb.x * v;
+                for (int fh = 0; fh < F1; fh += 4) {
+                    float4 dzv[4], yv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t base = ((n * F1 + fh + q) * C + c) * (int64_t)T + tc + t;
+                        dzv[q] = act ? *reinterpret_cast<const float4 *>(dz1 + base) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (bn_train) yv[q] = act ? *reinterpret_cast<const float4 *>(y1 + base) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    dys[t * F1 + f] = v;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 kb = bnb1[(int64_t)m * F1 + fh + q];
+                        float4 o;
+                        if (bn_train) {
+                            const float4 kf = bnf1[(int64_t)m * F1 + fh + q];
+                            o.x = kb.x * (dzv[q].x - kb.y - (yv[q].x - kf.x) * kf.y * kb.z);
+                            o.y = kb.x * (dzv[q].y - kb.y - (yv[q].y - kf.x) * kf.y * kb.z);
+                            o.z = kb.x * (dzv[q].z - kb.y - (yv[q].z - kf.x) * kf.y * kb.z);
+                            o.w = kb.x * (dzv[q].w - kb.y - (yv[q].w - kf.x) * kf.y * kb.z);
+                        } else {
+                            o = make_float4(kb.x * dzv[q].x, kb.x * dzv[q].y, kb.x * dzv[q].z, kb.x * dzv[q].w);
+                        }
+                        if (act) *reinterpret_cast<float4 *>(dys + (fh + q) * TW_TCH + t) = o;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < F1; ++f) {
+                    const float4 kb = bnb1[(int64_t)m * F1 + f];
+                    const float4 kf = bnf1[(int64_t)m * F1 + f];
+                    const int64_t base = ((n * F1 + f) * C + c) * (int64_t)T + tc;
+                    for (int t = lane; t < tn; t += 32) {
+                        float v = 0.f;
+                        if (tc + t < T) {
+                            v = dz1[base + t];
+                            if (bn_train) v = kb.x * (v - kb.y - (y1[base + t] - kf.x) * kf.y * kb.z);
+                            else v = kb.x * v;
+                        }
+                        dys[f * TW_TCH + t] = v;
+                    }
                 }
             }
             __syncwarp();
@@ -659,19 +787,18 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
                     float2 v = *reinterpret_cast<const float2 *>(xr + t + 2 * q);
                     xw[2 * q] = v.x; xw[2 * q + 1] = v.y;
                 }
+                float dv[F1][4];
 #pragma unroll
-                for (int tt = 0; tt < 4; ++tt) {
-                    float dv[F1];
+                for (int f = 0; f < F1; ++f) {
+                    float4 v = *reinterpret_cast<const float4 *>(dys + f * TW_TCH + t);
+                    dv[f][0] = v.x; dv[f][1] = v.y; dv[f][2] = v.z; dv[f][3] = v.w;
+                }
 #pragma unroll
-                    for (int q = 0; q < F1 / 4; ++q) {
-                        float4 v = *reinterpret_cast<const float4 *>(dys + (t + tt) * F1 + 4 * q);
-                        dv[4 * q] = v.x; dv[4 * q + 1] = v.y; dv[4 * q + 2] = v.z; dv[4 * q + 3] = v.w;
-                    }
+                for (int tt = 0; tt < 4; ++tt)
 #pragma unroll
                     for (int f = 0; f < F1; ++f)
 #pragma unroll
-                        for (int q = 0; q < RK; ++q) acc[f][q] = fmaf(dv[f], xw[tt + q], acc[f][q]);
-                }
+                        for (int q = 0; q < RK; ++q) acc[f][q] = fmaf(dv[f][tt], xw[tt + q], acc[f][q]);
             }
         }
     }

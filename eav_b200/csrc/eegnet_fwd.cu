@@ -215,6 +215,9 @@ int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_
 constexpr int DW_THREADS = 128;
 constexpr int DMAX = 8;
 
+// VEC = 4: each thread owns 4 consecutive time samples (128-bit loads/stores, needs T % 4 == 0);
+// VEC = 1: scalar fallback for any T.
+template <int VEC>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, int64_t pstride,
               int64_t oW2, const float4 *__restrict__ bn1, int B, int F1, int D, int C, int T,
@@ -222,34 +225,60 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
     extern __shared__ float w2s[];  // [D][C]
     __shared__ float red[DW_THREADS / 32][2 * DMAX];
     const int n = blockIdx.z, f = blockIdx.y, m = n / B;
-    const int t = blockIdx.x * DW_THREADS + threadIdx.x;
+    const int t = (blockIdx.x * DW_THREADS + threadIdx.x) * VEC;
     const int G = F1 * D;
     const float *W2 = params + (int64_t)m * pstride + oW2 + (int64_t)f * D * C;
     for (int i = threadIdx.x; i < D * C; i += DW_THREADS) w2s[i] = W2[i];
     const float4 st = bn1[(int64_t)m * F1 + f];
     __syncthreads();
-    float acc[DMAX];
+    float acc[DMAX][VEC];
 #pragma unroll
-    for (int dd = 0; dd < DMAX; ++dd) acc[dd] = 0.f;
+    for (int dd = 0; dd < DMAX; ++dd)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[dd][e] = 0.f;
     if (t < T) {
         const float *src = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T + t;
+#pragma unroll 6
         for (int c = 0; c < C; ++c) {
-            float v = fmaf(src[(int64_t)c * T], st.z, st.w);
-            float a = elu1 ? elu_f(v) : v;
+            float a[VEC];
+            if (VEC == 4) {
+                float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)c * T);
+                a[0] = v.x; a[1 % VEC] = v.y; a[2 % VEC] = v.z; a[3 % VEC] = v.w;
+            } else {
+                a[0] = src[(int64_t)c * T];
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                float v = fmaf(a[e], st.z, st.w);
+                a[e] = elu1 ? elu_f(v) : v;
+            }
 #pragma unroll
             for (int dd = 0; dd < DMAX; ++dd)
-                if (dd < D) acc[dd] = fmaf(w2s[dd * C + c], a, acc[dd]);
+                if (dd < D) {
+                    const float w = w2s[dd * C + c];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) acc[dd][e] = fmaf(w, a[e], acc[dd][e]);
+                }
         }
 #pragma unroll
         for (int dd = 0; dd < DMAX; ++dd)
-            if (dd < D) y2[((int64_t)n * G + f * D + dd) * (int64_t)T + t] = acc[dd];
+            if (dd < D) {
+                float *dst = y2 + ((int64_t)n * G + f * D + dd) * (int64_t)T + t;
+                if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(acc[dd][0], acc[dd][1 % VEC], acc[dd][2 % VEC], acc[dd][3 % VEC]);
+                else dst[0] = acc[dd][0];
+            }
     }
     if (part != nullptr) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
         for (int dd = 0; dd < DMAX; ++dd) {
-            float v = (t < T && dd < D) ? acc[dd] : 0.f;
-            float s = warp_sum(v), q = warp_sum(v * v);
+            float s = 0.f, q = 0.f;
+            if (t < T && dd < D) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { s += acc[dd][e]; q = fmaf(acc[dd][e], acc[dd][e], q); }
+            }
+            s = warp_sum(s);
+            q = warp_sum(q);
             if (lane == 0) { red[warp][2 * dd] = s; red[warp][2 * dd + 1] = q; }
         }
         __syncthreads();
@@ -264,12 +293,18 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
     }
 }
 
+int dw_fwd_tiles(const NetDims &d) { return (d.T & 3) == 0 ? cdiv(d.T, DW_THREADS * 4) : cdiv(d.T, DW_THREADS); }
+
 int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
                   float *y2, float *part, int *part_rows, cudaStream_t st) {
     EAV_REQUIRE(d.D <= DMAX, EAV_ERR_UNSUPPORTED, "dw_fwd: D=%d > %d unsupported", d.D, DMAX);
-    dim3 grid(cdiv(d.T, DW_THREADS), d.F1, d.N);
-    dw_fwd_kernel<<<grid, DW_THREADS, (size_t)d.D * d.C * sizeof(float), st>>>(
-        y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, d.variant == EAV_VARIANT_TOR, y2, part);
+    dim3 grid(dw_fwd_tiles(d), d.F1, d.N);
+    const size_t smem = (size_t)d.D * d.C * sizeof(float);
+    const int elu1 = d.variant == EAV_VARIANT_TOR;
+    if ((d.T & 3) == 0)
+        dw_fwd_kernel<4><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+    else
+        dw_fwd_kernel<1><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
     EAV_CUDA_LAUNCH_CHECK("dw_fwd");
     if (part_rows) *part_rows = d.B * grid.x;
     return 0;
@@ -293,7 +328,13 @@ __global__ void pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__r
         const float4 st = bn2[(int64_t)(n / B) * G + g];
         const float *src = y2 + ng * (int64_t)T + (int64_t)u * P1;
         float s = 0.f;
-        for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+        if (P1 == 4 && (T & 3) == 0) {       // one aligned 128-bit load per pooling window
+            const float4 v = *reinterpret_cast<const float4 *>(src);
+            s = elu_f(fmaf(v.x, st.z, st.w)) + elu_f(fmaf(v.y, st.z, st.w)) + elu_f(fmaf(v.z, st.z, st.w)) +
+                elu_f(fmaf(v.w, st.z, st.w));
+        } else {
+            for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+        }
         s *= 1.f / (float)P1;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[i] ? s * inv_keep : 0.f;
         else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 1u, (uint64_t)i, p_drop) ? s * inv_keep : 0.f;

@@ -56,6 +56,8 @@ int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index
                         const float *y1, const float4 *bnf1, const float4 *bnb1, float *part,
                         float *grads, cudaStream_t st);
 
+int dw_fwd_tiles(const NetDims &d);   // time tiles per (sample, filter) of dw_fwd == BN2 partial rows per sample
+
 // ---- small ops -------------------------------------------------------------------
 int launch_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_stride,
                        int64_t rows_per_group, int64_t group_stride, float maxnorm, cudaStream_t st);

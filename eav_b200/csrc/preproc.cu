@@ -25,74 +25,188 @@ constexpr int MAX_TAPS = 128;
 
 struct FirTaps { float h[MAX_TAPS]; double sum; };
 
-// Generic-shape tile loader: xs[s] = x_seq[i0 + s] for s in [0, n_in), zero outside the record.
+// Tile loader: xs[s] = x_seq[i0 + s] for s in [0, n_in), zero outside the record.  The
+// continuous index is mapped to (trial, offset) ONCE per thread and then advanced
+// incrementally (no per-element 64-bit division).  When every quantity is even the tile is
+// fetched as 8-byte pairs (a pair never straddles a trial boundary): LDG.64 -> STS.64.
 template <typename TIn>
 __device__ __forceinline__ void fir_load_tile(const TIn *__restrict__ raw, int64_t seq_base, int64_t ch_off,
                                               int trial_len, int64_t trial_stride, int64_t n_seq, int64_t i0,
                                               int n_in, float *xs) {
-    for (int s = threadIdx.x; s < n_in; s += blockDim.x) {
-        int64_t i = i0 + s;
-        float v = 0.f;
-        if (i >= 0 && i < n_seq) {
-            int64_t tr = i / trial_len;
-            int off = (int)(i - tr * trial_len);
-            v = (float)raw[seq_base + tr * trial_stride + ch_off + off];
+    const bool pairs = sizeof(TIn) == 4 && ((trial_len | n_in) & 1) == 0 && (i0 & 1) == 0 &&
+                       (((seq_base + ch_off) | trial_stride) & 1) == 0 && (reinterpret_cast<uintptr_t>(raw) & 7) == 0;
+    const TIn *base = raw + seq_base + ch_off;
+    if (pairs) {
+        const int step = 2 * blockDim.x;
+        int64_t i = i0 + 2 * threadIdx.x;
+        // floor division that also works for the (small) negative head of the first tile
+        int64_t tr = (i >= 0) ? i / trial_len : -1;
+        int off = (int)(i - tr * trial_len);
+        for (int s = 2 * threadIdx.x; s < n_in; s += step) {
+            float2 v = make_float2(0.f, 0.f);
+            if (i >= 0 && i < n_seq) v = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(base) + tr * trial_stride + off);
+            *reinterpret_cast<float2 *>(xs + s) = v;
+            i += step;
+            off += step;
+            while (off >= trial_len) { off -= trial_len; ++tr; }
         }
-        xs[s] = v;
+    } else {
+        const int step = blockDim.x;
+        int64_t i = i0 + threadIdx.x;
+        int64_t tr = (i >= 0) ? i / trial_len : -((-i + trial_len - 1) / trial_len);
+        int off = (int)(i - tr * trial_len);
+        for (int s = threadIdx.x; s < n_in; s += step) {
+            float v = 0.f;
+            if (i >= 0 && i < n_seq) v = (float)base[tr * trial_stride + off];
+            xs[s] = v;
+            i += step;
+            off += step;
+            while (off >= trial_len) { off -= trial_len; ++tr; }
+        }
     }
 }
 
+// ---- TMA (cp.async.bulk) + mbarrier helpers -------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion is signalled on `bar`.
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Compile-time expansion of the FIR inner product (template recursion instead of
+// `#pragma unroll`, whose size heuristics silently refused the 1120-iteration nest):
+// II = offset of one staged input sample relative to x[DOWN*j - H]; for each of the FIR_R
+// outputs of the thread the tap index t = DOWN*r + 2H - II is a constant, so every FFMA
+// takes its tap from a uniform register.
+template <int DOWN, int NTAPS, bool SKIP, int II>
+__device__ __forceinline__ void fir_one_input(const FirTaps &taps, float v, float (&acc0)[FIR_R], float (&acc1)[FIR_R]) {
+    constexpr int H = (NTAPS - 1) / 2;
+    if constexpr (II >= 0) {
+#pragma unroll
+        for (int r = 0; r < FIR_R; ++r) {
+            const int t = DOWN * r + 2 * H - II;
+            const bool zero_tap = SKIP && t != H && ((t - H) % DOWN) == 0;
+            if (t >= 0 && t < NTAPS && !zero_tap) {
+                if (II & 1) acc1[r] = fmaf(taps.h[t], v, acc1[r]);
+                else acc0[r] = fmaf(taps.h[t], v, acc0[r]);
+            }
+        }
+    }
+}
+template <int DOWN, int NTAPS, bool SKIP, int LEAD, int Q, int NQ>
+struct FirSteps {
+    static __device__ __forceinline__ void run(const FirTaps &taps, const float *xw, float m, float (&acc0)[FIR_R],
+                                               float (&acc1)[FIR_R]) {
+        const float4 v4 = *reinterpret_cast<const float4 *>(xw + 4 * Q);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 0 - LEAD>(taps, v4.x - m, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 1 - LEAD>(taps, v4.y - m, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 2 - LEAD>(taps, v4.z - m, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 3 - LEAD>(taps, v4.w - m, acc0, acc1);
+        FirSteps<DOWN, NTAPS, SKIP, LEAD, Q + 1, NQ>::run(taps, xw, m, acc0, acc1);
+    }
+};
+template <int DOWN, int NTAPS, bool SKIP, int LEAD, int NQ>
+struct FirSteps<DOWN, NTAPS, SKIP, LEAD, NQ, NQ> {
+    static __device__ __forceinline__ void run(const FirTaps &, const float *, float, float (&)[FIR_R], float (&)[FIR_R]) {}
+};
+
 // Fully unrolled decimating FIR: DOWN and NTAPS are compile-time so every tap index is
-// static and the taps are read straight from the kernel-parameter constant bank.
+// static and the taps sit in uniform registers fed from the kernel-parameter constant bank.
+// Staging: xs[s] = x[DOWN*j0 - H - 2 + s].  The 2-sample lead makes both the trial body
+// (a multiple of 16 B into the tile) and every thread window (DOWN*FIR_R*4 B apart) 16-byte
+// aligned, so in the trial-aligned case one elected thread stages the whole tile with three
+// TMA bulk copies (tail of the previous trial, the trial, head of the next trial) on an
+// mbarrier, and the compute threads read it back with LDS.128.
 // Each thread removes a local offset m (its first window sample) before the fp32
 // accumulation and adds m*sum(h) back in fp64: the low-frequency content (drift / DC)
 // that dominates raw EEG magnitude then costs no fp32 mantissa (error ~2e-6 of channel
 // RMS after the band-pass instead of ~1e-5).
-template <typename TIn, int DOWN, int NTAPS>
+// SKIP: taps at distance k*DOWN from the centre are the sinc zeros of the decimation
+// filter (|h| ~ 7.6e-18); when the host verified that they are < 1e-15 |h_centre| they are
+// compiled out (20 % fewer FFMA), a perturbation far below one fp64 ulp of the result.
+template <typename TIn, int DOWN, int NTAPS, bool SKIP>
 __global__ void __launch_bounds__(FIR_THREADS)
 fir_decimate_kernel(const TIn *__restrict__ raw, const __grid_constant__ FirTaps taps, int n_trials, int n_chans,
-                    int trial_len, int64_t n_dec, int tile_out, float *__restrict__ dec) {
-    extern __shared__ __align__(16) float xs[];
+                    int trial_len, int64_t n_dec, int tile_out, int use_tma, float *__restrict__ dec) {
+    extern __shared__ __align__(128) float xs[];
+    __shared__ __align__(8) uint64_t bar;
     constexpr int H = (NTAPS - 1) / 2;
-    constexpr int WIN = DOWN * (FIR_R - 1) + NTAPS;            // window per thread (136)
+    constexpr int LEAD = 2;
+    constexpr int WIN = DOWN * (FIR_R - 1) + NTAPS + LEAD;     // window per thread (138)
     constexpr int WIN4 = (WIN + 3) / 4 * 4;
     const int s = blockIdx.z, c = blockIdx.y;
     const int64_t j0 = (int64_t)blockIdx.x * tile_out;
     const int64_t n_seq = (int64_t)n_trials * trial_len;
-    const int n_in = DOWN * tile_out + NTAPS + 8;             // smem extent (covers every active thread's WIN4)
-    fir_load_tile<TIn>(raw, (int64_t)s * n_trials * n_chans * trial_len, (int64_t)c * trial_len, trial_len,
-                       (int64_t)n_chans * trial_len, n_seq, (int64_t)DOWN * j0 - H, n_in, xs);
-    __syncthreads();
+    const int n_in = (DOWN * (tile_out - FIR_R) + WIN4 + 3) & ~3;   // smem extent every active window stays inside
+    const int64_t i0 = (int64_t)DOWN * j0 - H - LEAD;
+    const int64_t seq_base = (int64_t)s * n_trials * n_chans * trial_len;
+    const int64_t ch_off = (int64_t)c * trial_len, tstride = (int64_t)n_chans * trial_len;
+    if (use_tma) {
+        // tile == trial blockIdx.x: head = last (H+LEAD) samples of the previous trial, body = the
+        // trial, tail = first samples of the next trial.  Out-of-record parts are zero-filled.
+        const int head = H + LEAD, tail = n_in - head - trial_len;
+        const int64_t tr = blockIdx.x;
+        const float *body = reinterpret_cast<const float *>(raw) + seq_base + tr * tstride + ch_off;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (tr == 0) for (int i = threadIdx.x; i < head; i += blockDim.x) xs[i] = 0.f;
+        if (tr == n_trials - 1) for (int i = threadIdx.x; i < tail; i += blockDim.x) xs[head + trial_len + i] = 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t bytes = (uint32_t)trial_len * 4u;
+            if (tr > 0) bytes += (uint32_t)head * 4u;
+            if (tr < n_trials - 1) bytes += (uint32_t)tail * 4u;
+            mbar_expect_tx(&bar, bytes);
+            if (tr > 0) tma_load_1d(xs, body - tstride + (trial_len - head), (uint32_t)head * 4u, &bar);
+            tma_load_1d(xs + head, body, (uint32_t)trial_len * 4u, &bar);
+            if (tr < n_trials - 1) tma_load_1d(xs + head + trial_len, body + tstride, (uint32_t)tail * 4u, &bar);
+            mbar_wait(&bar, 0);     // only the issuing thread polls the mbarrier ...
+        }
+        __syncthreads();            // ... everyone else sleeps on the hardware barrier (no issue slots burnt)
+    } else {
+        fir_load_tile<TIn>(raw, seq_base, ch_off, trial_len, tstride, n_seq, i0, n_in, xs);
+        __syncthreads();
+    }
 
     const int jl = threadIdx.x * FIR_R;
     if (jl >= tile_out) return;
-    const float *xw = xs + DOWN * jl;                          // 16B aligned when DOWN*FIR_R % 4 == 0
-    const float m = xw[0];
+    const float *xw = xs + DOWN * jl;                          // 16B aligned: DOWN*FIR_R % 4 == 0
+    const float m = xw[LEAD];
     float acc0[FIR_R], acc1[FIR_R];
 #pragma unroll
     for (int r = 0; r < FIR_R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < WIN4 / 4; ++q) {
-        float4 v4 = *reinterpret_cast<const float4 *>(xw + 4 * q);
-        const float v[4] = {v4.x - m, v4.y - m, v4.z - m, v4.w - m};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int ii = 4 * q + e;
-#pragma unroll
-            for (int r = 0; r < FIR_R; ++r) {
-                const int t = DOWN * r + 2 * H - ii;           // tap index for output r, input ii
-                if (t >= 0 && t < NTAPS) {
-                    if (ii & 1) acc1[r] = fmaf(taps.h[t], v[e], acc1[r]);
-                    else acc0[r] = fmaf(taps.h[t], v[e], acc0[r]);
-                }
-            }
-        }
-    }
+    FirSteps<DOWN, NTAPS, SKIP, LEAD, 0, WIN4 / 4>::run(taps, xw, m, acc0, acc1);
     float *dst = dec + ((int64_t)s * n_chans + c) * n_dec + j0 + jl;
     const double md = (double)m * taps.sum;
+    float o[FIR_R];
 #pragma unroll
-    for (int r = 0; r < FIR_R; ++r)
-        if (jl + r < tile_out && j0 + jl + r < n_dec) dst[r] = (float)((double)(acc0[r] + acc1[r]) + md);
+    for (int r = 0; r < FIR_R; ++r) o[r] = (float)((double)(acc0[r] + acc1[r]) + md);
+    if (jl + FIR_R <= tile_out && j0 + jl + FIR_R <= n_dec && ((n_dec | tile_out) & 3) == 0) {
+        reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < FIR_R; ++r)
+            if (jl + r < tile_out && j0 + jl + r < n_dec) dst[r] = o[r];
+    }
 }
 
 // Any (down, n_taps): one output per thread, taps from the constant bank, fp32 with the same
@@ -178,18 +292,26 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
     const int64_t ep_stride = (int64_t)n_chans * ep_len;
     __syncthreads();
 
+    // Software pipeline: the 32 rows of the NEXT 32-sample tile are fetched into registers
+    // (32 independent 128-byte row reads per warp in flight) while the current tile is being
+    // filtered out of shared memory.
+    float pre[32];
+    auto fetch = [&](int i0) {
+        const int nt = min(SOS_TILE, chunk_len - i0);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int64_t src = row_src[warp * 32 + r];
+            pre[r] = (src >= 0 && lane < nt) ? dec[src + i0 + lane] : 0.f;
+        }
+    };
+    fetch(0);
     for (int i0 = 0; i0 < chunk_len; i0 += SOS_TILE) {
         const int nt = min(SOS_TILE, chunk_len - i0);
         __syncwarp();
-        // each warp stages the 32 chunks its own lanes walk: lane = sample -> 128 B per row
-        for (int r = 0; r < 32; ++r) {
-            const int row = warp * 32 + r;
-            const int64_t src = row_src[row];
-            float v = 0.f;
-            if (src >= 0 && lane < nt) v = dec[src + i0 + lane];
-            tile[row][lane] = v;
-        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) tile[warp * 32 + r][lane] = pre[r];
         __syncwarp();
+        if (i0 + SOS_TILE < chunk_len) fetch(i0 + SOS_TILE);
         if (my_ok) {
 #pragma unroll 4
             for (int i = 0; i < nt; ++i) {
@@ -208,6 +330,7 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
             __syncwarp();
             const int i = i0 + lane;
             const int q = i / ep_len, off = i - q * ep_len;
+#pragma unroll 8
             for (int r = 0; r < 32; ++r) {
                 const int row = warp * 32 + r;
                 if (row_src[row] >= 0 && lane < nt && q < n_sub)
@@ -310,22 +433,36 @@ static int run_sos(const eav_preproc_cfg *c, const float *dec, const SosCoef &co
     return 0;
 }
 
+template <typename TIn, bool SKIP>
+static int launch_fir_5_101(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, float *dec, cudaStream_t st) {
+    const int chunk = c->trial_len / c->down;
+    const int64_t n_dec = (int64_t)c->n_trials * chunk;
+    const int tile_out = chunk <= FIR_OT ? chunk : FIR_OT;
+    const int tiles = (int)cdiv64(n_dec, tile_out);
+    const size_t smem = (size_t)(5 * FIR_OT + 160) * sizeof(float);
+    // TMA staging needs: float input, one trial per tile, 16-byte aligned rows and tile geometry
+    int use_tma = 0;
+    if (sizeof(TIn) == 4 && tile_out == chunk && (tile_out % FIR_R) == 0 && (c->trial_len & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && c->trial_len >= 64)
+        use_tma = 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(fir_decimate_kernel<TIn, 5, 101, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    fir_decimate_kernel<TIn, 5, 101, SKIP><<<dim3(tiles, c->n_chans, c->n_subjects), FIR_THREADS, smem, st>>>(
+        raw, taps, c->n_trials, c->n_chans, c->trial_len, n_dec, tile_out, use_tma, dec);
+    return 0;
+}
+
 template <typename TIn>
-static int run_fir(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, float *dec, cudaStream_t st) {
+static int run_fir(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, bool skip_zero_taps, float *dec,
+                   cudaStream_t st) {
     const int chunk = c->trial_len / c->down;
     const int64_t n_dec = (int64_t)c->n_trials * chunk;
     if (c->down == 5 && c->n_taps == 101) {
-        const int tile_out = chunk <= FIR_OT ? chunk : FIR_OT;
-        const int tiles = (int)cdiv64(n_dec, tile_out);
-        size_t smem = (size_t)(5 * FIR_OT + 101 + 8) * sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(fir_decimate_kernel<float, 5, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            cudaFuncSetAttribute(fir_decimate_kernel<double, 5, 101>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-            attr_set = true;
-        }
-        fir_decimate_kernel<TIn, 5, 101><<<dim3(tiles, c->n_chans, c->n_subjects), FIR_THREADS, smem, st>>>(
-            raw, taps, c->n_trials, c->n_chans, c->trial_len, n_dec, tile_out, dec);
+        if (skip_zero_taps) launch_fir_5_101<TIn, true>(c, raw, taps, dec, st);
+        else launch_fir_5_101<TIn, false>(c, raw, taps, dec, st);
     } else {
         fir_decimate_generic_kernel<TIn><<<dim3((unsigned)cdiv64(n_dec, FIR_THREADS), c->n_chans, c->n_subjects),
                                           FIR_THREADS, 0, st>>>(raw, taps, c->n_taps, c->down, c->n_trials,
@@ -426,8 +563,15 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
         EAV_CUDA_LAUNCH_CHECK("invert_slots");
     }
 
-    if (cfg->raw_is_f64) rc = run_fir<double>(cfg, reinterpret_cast<const double *>(raw), ft, dec, st);
-    else rc = run_fir<float>(cfg, reinterpret_cast<const float *>(raw), ft, dec, st);
+    // sinc zeros of the decimation filter (taps k*down away from the centre): compile them out when negligible
+    bool skip_zero = true;
+    {
+        const int Hh = (cfg->n_taps - 1) / 2;
+        for (int t = 0; t < cfg->n_taps; ++t)
+            if (t != Hh && ((t - Hh) % cfg->down) == 0 && fabs(taps[t]) > 1e-15 * fabs(taps[Hh])) skip_zero = false;
+    }
+    if (cfg->raw_is_f64) rc = run_fir<double>(cfg, reinterpret_cast<const double *>(raw), ft, skip_zero, dec, st);
+    else rc = run_fir<float>(cfg, reinterpret_cast<const float *>(raw), ft, skip_zero, dec, st);
     if (rc) return rc;
 
     switch (NSEC) {
