@@ -28,7 +28,8 @@ class EegnetCfg(Structure):
                                         "kern_len2", "pool1", "pool2", "n_classes", "variant", "bn_train",
                                         "dropout_mode", "param_stride", "bn_stride")]
                 + [(n, c_float) for n in ("dropout_p", "bn_eps", "bn_momentum", "norm_rate")]
-                + [("seed", c_uint64), ("step", c_uint64), ("step_device_ptr", c_uint64)])
+                + [("seed", c_uint64), ("step", c_uint64), ("step_device_ptr", c_uint64)]
+                + [("dp_world", c_int32), ("reserved", c_int32)])
 
 
 # every symbol include/eav_b200.h declares: (restype, argtypes)
@@ -54,6 +55,7 @@ SYMBOLS = {
     "eav_eegnet_stage_name": (c_char_p, [c_int]),
     "eav_eegnet_run_stage": (c_int, [POINTER(EegnetCfg), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "eav_eegnet_stage_allreduce": (c_int, [POINTER(EegnetCfg), c_int, POINTER(c_size_t), POINTER(c_size_t)]),
     "eav_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_float, c_float,
                               c_float, c_void_p]),
     "eav_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,

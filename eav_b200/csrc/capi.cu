@@ -38,6 +38,7 @@ int make_dims(const eav_eegnet_cfg *c, NetDims *d) {
     d->p_drop = c->dropout_p; d->eps = c->bn_eps; d->momentum = c->bn_momentum; d->norm_rate = c->norm_rate;
     d->seed = c->seed; d->step = c->step;
     d->step_ptr = reinterpret_cast<const unsigned long long *>(c->step_device_ptr);
+    d->dp_world = c->dp_world > 1 ? c->dp_world : 1;
     if (d->p_drop == 0.f) d->dropout_mode = EAV_DROPOUT_NONE;
     int64_t o = 0;
     d->oW1 = o; o += (int64_t)d->F1 * d->K1;
@@ -86,6 +87,11 @@ WsLayout make_ws_layout(const NetDims &d) {
     w.dz = take(N * d.NC);
     w.bnf1 = take((size_t)d.M * d.F1 * 4); w.bnf2 = take((size_t)d.M * d.G * 4); w.bnf3 = take((size_t)d.M * d.F2 * 4);
     w.bnb1 = take((size_t)d.M * d.F1 * 4); w.bnb2 = take((size_t)d.M * d.G * 4); w.bnb3 = take((size_t)d.M * d.F2 * 4);
+    {   // float64 BN sums, 6 slots (fwd 1..3, bwd 1..3), each [M][max channels][2]
+        int mc = d.F1 > d.G ? d.F1 : d.G; if (d.F2 > mc) mc = d.F2;
+        w.bnsum_slot = align_up((size_t)d.M * mc * 2 * sizeof(double), 256);
+        w.bnsum = take(6 * w.bnsum_slot / sizeof(float));
+    }
     // BN partial sums (largest user)
     size_t pa = 0;
     pa = max_sz(pa, N * cdiv(d.C, 4) * cdiv(d.T, 512) * 2 * d.F1);        // tconv_fwd
@@ -175,17 +181,31 @@ extern "C" int eav_eegnet_workspace_offsets(const eav_eegnet_cfg *cfg, size_t *o
 // a previous full pass left in the workspace (per-kernel timing / profiling hook).
 // ---------------------------------------------------------------------------------
 enum {
-    ST_TCONV_FWD = 0, ST_BN1, ST_DW_FWD, ST_RENORM_W2, ST_BN2, ST_POOL1_FWD, ST_SEPCONV_FWD, ST_BN3,
-    ST_TAIL_FWD, ST_RENORM_WD,
-    ST_TAIL_BWD, ST_DENSE_BWD_W, ST_BN3_BWD, ST_SEPCONV_BWD_DX, ST_SEPCONV_BWD_DW, ST_POOL1_BWD, ST_BN2_BWD,
-    ST_DW_BWD, ST_BN1_BWD, ST_TCONV_BWD_DW, ST_COUNT
+    ST_TCONV_FWD = 0, ST_BN1_REDUCE, ST_BN1, ST_DW_FWD, ST_RENORM_W2, ST_BN2_REDUCE, ST_BN2, ST_POOL1_FWD,
+    ST_SEPCONV_FWD, ST_BN3_REDUCE, ST_BN3, ST_TAIL_FWD, ST_RENORM_WD,
+    ST_TAIL_BWD, ST_DENSE_BWD_W, ST_BN3_BWD_REDUCE, ST_BN3_BWD, ST_SEPCONV_BWD_DX, ST_SEPCONV_BWD_DW, ST_POOL1_BWD,
+    ST_BN2_BWD_REDUCE, ST_BN2_BWD, ST_DW_BWD, ST_BN1_BWD_REDUCE, ST_BN1_BWD, ST_TCONV_BWD_DW, ST_COUNT
 };
 static const int ST_FWD_END = ST_TAIL_BWD;
 static const char *kStageNames[ST_COUNT] = {
-    "tconv_fwd", "bn1_finalize", "dw_fwd", "renorm_depthwise", "bn2_finalize", "pool1_fwd", "sepconv_fwd",
-    "bn3_finalize", "tail_fwd", "renorm_dense",
-    "tail_bwd", "dense_bwd_w", "bn3_bwd_finalize", "sepconv_bwd_dx", "sepconv_bwd_dw", "pool1_bwd",
-    "bn2_bwd_finalize", "dw_bwd", "bn1_bwd_finalize", "tconv_bwd_dw"};
+    "tconv_fwd", "bn1_reduce", "bn1_finalize", "dw_fwd", "renorm_depthwise", "bn2_reduce", "bn2_finalize",
+    "pool1_fwd", "sepconv_fwd", "bn3_reduce", "bn3_finalize", "tail_fwd", "renorm_dense",
+    "tail_bwd", "dense_bwd_w", "bn3_bwd_reduce", "bn3_bwd_finalize", "sepconv_bwd_dx", "sepconv_bwd_dw",
+    "pool1_bwd", "bn2_bwd_reduce", "bn2_bwd_finalize", "dw_bwd", "bn1_bwd_reduce", "bn1_bwd_finalize",
+    "tconv_bwd_dw"};
+
+// which BatchNorm layer (1..3) a *_REDUCE stage belongs to, and whether it is a backward one
+static bool reduce_stage(int stage, int *layer, bool *bwd) {
+    switch (stage) {
+        case ST_BN1_REDUCE: *layer = 1; *bwd = false; return true;
+        case ST_BN2_REDUCE: *layer = 2; *bwd = false; return true;
+        case ST_BN3_REDUCE: *layer = 3; *bwd = false; return true;
+        case ST_BN1_BWD_REDUCE: *layer = 1; *bwd = true; return true;
+        case ST_BN2_BWD_REDUCE: *layer = 2; *bwd = true; return true;
+        case ST_BN3_BWD_REDUCE: *layer = 3; *bwd = true; return true;
+        default: return false;
+    }
+}
 
 struct StageArgs {
     const float *x; const int32_t *x_index; float *params; float *bn_state; const uint8_t *mask1, *mask2;
@@ -202,21 +222,36 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     const int rows1 = d.B * cdiv(d.C, 4) * cdiv(d.T, 512);
     const int rows2 = d.B * dw_fwd_tiles(d);
     const int rows3 = tor ? cdiv(d.B, 2) * cdiv(d.T4, 128) : d.B;
+    // data-parallel (dp_world > 1) train-mode BN: statistics go through float64 sums that the
+    // caller all-reduces between the *_reduce stage and the *_finalize stage
+    const bool dp_bn = d.dp_world > 1 && d.bn_train;
+    auto sums = [&](int layer, bool bwd) -> double * {
+        return reinterpret_cast<double *>(reinterpret_cast<char *>(workspace) + w.bnsum + ((bwd ? 3 : 0) + layer - 1) * w.bnsum_slot);
+    };
+    const double W = (double)d.dp_world;
+    {
+        int layer; bool bwd;
+        if (reduce_stage(stage, &layer, &bwd)) {
+            if (!dp_bn) return 0;
+            const int rows = bwd ? d.B : (layer == 1 ? rows1 : layer == 2 ? rows2 : rows3);
+            return launch_bn_reduce(d, layer, part, rows, sums(layer, bwd), st);
+        }
+    }
     switch (stage) {
         case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.y1), pstat, nullptr, st);
-        case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, (double)d.B * d.C * d.T, a.params, a.bn_state, WS(float4, w.bnf1), st);
+        case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, W * d.B * d.C * d.T, dp_bn ? sums(1, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf1), st);
         case ST_DW_FWD: return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, st);
         case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34)
             if (tor && d.norm_rate > 0.f)
                 return launch_renorm_rows(a.params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st);
             return 0;
-        case ST_BN2: return launch_bn_finalize(d, 2, part, rows2, (double)d.B * d.T, a.params, a.bn_state, WS(float4, w.bnf2), st);
+        case ST_BN2: return launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, dp_bn ? sums(2, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st);
         case ST_POOL1_FWD: return launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.d1), st);
         case ST_SEPCONV_FWD:
             if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3), pstat, nullptr, st);
             TRY(launch_dwt_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3d), st));
             return launch_pw_fwd(d, WS(float, w.y3d), a.params, WS(float, w.y3), pstat, nullptr, st);
-        case ST_BN3: return launch_bn_finalize(d, 3, part, rows3, (double)d.B * d.T4, a.params, a.bn_state, WS(float4, w.bnf3), st);
+        case ST_BN3: return launch_bn_finalize(d, 3, part, rows3, W * d.B * d.T4, dp_bn ? sums(3, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf3), st);
         case ST_TAIL_FWD:
             return launch_tail_fwd(d, WS(float, w.y3), WS(float4, w.bnf3), a.mask2, a.params, WS(float, w.feat), a.out, WS(float, w.probs), st);
         case ST_RENORM_WD:   // hook on dense (EEGNet_tor.py:47-48)
@@ -228,7 +263,7 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
                                    WS(float, w.dz), WS(float, w.dz3), part, st);
         case ST_DENSE_BWD_W: return launch_dense_bwd_w(d, WS(float, w.feat), WS(float, w.dz), a.grads, st);
         case ST_BN3_BWD:
-            return launch_bn_bwd_finalize(d, 3, part, d.B, (double)d.B * d.T4, a.params, WS(float4, w.bnf3), WS(float4, w.bnb3), a.grads, st);
+            return launch_bn_bwd_finalize(d, 3, part, d.B, W * d.B * d.T4, dp_bn ? sums(3, true) : nullptr, a.params, WS(float4, w.bnf3), WS(float4, w.bnb3), a.grads, st);
         case ST_SEPCONV_BWD_DX:
             if (tor)
                 return launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
@@ -243,12 +278,12 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_POOL1_BWD:
             return launch_pool1_bwd(d, WS(float, w.dd1), WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.dz2), part, st);
         case ST_BN2_BWD:
-            return launch_bn_bwd_finalize(d, 2, part, d.B, (double)d.B * d.T, a.params, WS(float4, w.bnf2), WS(float4, w.bnb2), a.grads, st);
+            return launch_bn_bwd_finalize(d, 2, part, d.B, W * d.B * d.T, dp_bn ? sums(2, true) : nullptr, a.params, WS(float4, w.bnf2), WS(float4, w.bnb2), a.grads, st);
         case ST_DW_BWD:
             return launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
                                  WS(float4, w.bnf1), a.params, WS(float, w.dz1), partw2, part, a.grads, st);
         case ST_BN1_BWD:
-            return launch_bn_bwd_finalize(d, 1, part, d.B, (double)d.B * d.C * d.T, a.params, WS(float4, w.bnf1), WS(float4, w.bnb1), a.grads, st);
+            return launch_bn_bwd_finalize(d, 1, part, d.B, W * d.B * d.C * d.T, dp_bn ? sums(1, true) : nullptr, a.params, WS(float4, w.bnf1), WS(float4, w.bnb1), a.grads, st);
         case ST_TCONV_BWD_DW:
             return launch_tconv_bwd_dw(d, a.x, a.x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
                                        partw, a.grads, st);
@@ -285,6 +320,22 @@ extern "C" int eav_eegnet_stage_count(void) { return ST_COUNT; }
 extern "C" int eav_eegnet_stage_forward_end(void) { return ST_FWD_END; }
 extern "C" const char *eav_eegnet_stage_name(int stage) { return (stage >= 0 && stage < ST_COUNT) ? kStageNames[stage] : ""; }
 
+extern "C" int eav_eegnet_stage_allreduce(const eav_eegnet_cfg *cfg, int stage, size_t *offset_bytes, size_t *n_doubles) {
+    NetDims d;
+    TRY(make_dims(cfg, &d));
+    EAV_REQUIRE(offset_bytes && n_doubles, EAV_ERR_BAD_ARG, "stage_allreduce: null pointer");
+    *offset_bytes = 0;
+    *n_doubles = 0;
+    int layer; bool bwd;
+    if (d.dp_world > 1 && d.bn_train && reduce_stage(stage, &layer, &bwd)) {
+        const WsLayout w = make_ws_layout(d);
+        const int ch = layer == 1 ? d.F1 : layer == 2 ? d.G : d.F2;
+        *offset_bytes = w.bnsum + ((bwd ? 3 : 0) + layer - 1) * w.bnsum_slot;
+        *n_doubles = (size_t)d.M * ch * 2;
+    }
+    return 0;
+}
+
 extern "C" int eav_eegnet_run_stage(const eav_eegnet_cfg *cfg, int stage, const float *x, const int32_t *x_index,
                                     float *params, float *bn_state, const uint8_t *mask1, const uint8_t *mask2,
                                     float *out, const float *dout, float *grads, void *workspace,
@@ -309,6 +360,8 @@ extern "C" int eav_eegnet_forward(const eav_eegnet_cfg *cfg, const float *x, con
     StageArgs a = {x, x_index, params, bn_state, mask1, mask2, out, nullptr, nullptr, workspace};
     TRY(check_common(d, w, a, workspace_bytes, "eegnet_forward"));
     EAV_REQUIRE(bn_state && out, EAV_ERR_BAD_ARG, "eegnet_forward: null pointer");
+    EAV_REQUIRE(!(d.dp_world > 1 && d.bn_train), EAV_ERR_UNSUPPORTED,
+                "eegnet_forward: dp_world > 1 with train-mode BN must be driven stage by stage (eav_eegnet_run_stage + eav_eegnet_stage_allreduce)");
     for (int s = 0; s < ST_FWD_END; ++s) TRY(run_stage(d, w, s, a, (cudaStream_t)stream));
     return 0;
 }
@@ -323,6 +376,8 @@ extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, co
     StageArgs a = {x, x_index, const_cast<float *>(params), nullptr, mask1, mask2, nullptr, dout, grads, workspace};
     TRY(check_common(d, w, a, workspace_bytes, "eegnet_backward"));
     EAV_REQUIRE(dout && grads, EAV_ERR_BAD_ARG, "eegnet_backward: null pointer");
+    EAV_REQUIRE(!(d.dp_world > 1 && d.bn_train), EAV_ERR_UNSUPPORTED,
+                "eegnet_backward: dp_world > 1 with train-mode BN must be driven stage by stage");
     cudaStream_t st = (cudaStream_t)stream;
     // The weight gradients of the dense layer and of the block-2 conv do not feed the rest of
     // the chain: they run on a forked stream (works under stream capture too) and fill the SM

@@ -83,6 +83,7 @@ struct NetDims {
     int C, T, K1, F1, D, G; // G = F1*D
     int F2, K2, P1, P2, T4, T32, NC, FEAT;
     int variant, bn_train, dropout_mode;
+    int dp_world;           // data-parallel replicas of one model (1 = single device)
     int pad1l, pad2l;       // 'same' left paddings
     float p_drop, eps, momentum, norm_rate;
     uint64_t seed, step;
@@ -103,6 +104,8 @@ struct WsLayout {
     // offsets in BYTES from the workspace base
     size_t y1, y2, d1, y3d, y3, feat, probs, dz;      // saved activations
     size_t bnf1, bnf2, bnf3, bnb1, bnb2, bnb3;         // float4 per (m, ch)
+    size_t bnsum;                                      // double [6 slots][M][max ch][2]: BN sums for the dp all-reduce
+    size_t bnsum_slot;                                 // bytes per slot
     size_t part;                                       // BatchNorm partial sums
     size_t partw;                                      // weight-gradient partials: temporal conv (dW1)
     size_t partw2, partw3;                             // ... depthwise (dW2), block-2 conv (dW3): separate so the

@@ -121,21 +121,29 @@ int launch_dense_bwd_w(const NetDims &d, const float *feat, const float *dz, flo
 // Writes d(gamma) = sum dz*xhat, d(beta) = sum dz and the {k, c1, c2} block.
 // =================================================================================
 __global__ void bn_bwd_finalize_kernel(const float *__restrict__ part, int rows_per_model, int ch,
-                                       double count, const float *__restrict__ params, int64_t pstride,
+                                       double count, const double *__restrict__ sums, double grad_scale,
+                                       const float *__restrict__ params, int64_t pstride,
                                        int64_t og, int64_t ob, const float4 *__restrict__ bnf, int bn_train,
                                        float4 *__restrict__ bnb, float *__restrict__ grads) {
     const int c = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
-    const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
-    for (int r = lane; r < rows_per_model; r += 32) {
-        s1 += (double)p[((int64_t)r * ch + c) * 2];
-        s2 += (double)p[((int64_t)r * ch + c) * 2 + 1];
+    if (sums != nullptr) {              // already reduced (and all-reduced across replicas)
+        s1 = sums[((int64_t)m * ch + c) * 2];
+        s2 = sums[((int64_t)m * ch + c) * 2 + 1];
+    } else {
+        const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
+        for (int r = lane; r < rows_per_model; r += 32) {
+            s1 += (double)p[((int64_t)r * ch + c) * 2];
+            s2 += (double)p[((int64_t)r * ch + c) * 2 + 1];
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
     if (lane == 0) {
-        grads[(int64_t)m * pstride + og + c] = (float)s2;
-        grads[(int64_t)m * pstride + ob + c] = (float)s1;
+        // grad_scale = 1/dp_world when the sums are global: the caller's gradient all-reduce (sum)
+        // then restores exactly the global d(gamma), d(beta)
+        grads[(int64_t)m * pstride + og + c] = (float)(s2 * grad_scale);
+        grads[(int64_t)m * pstride + ob + c] = (float)(s1 * grad_scale);
         float k = params[(int64_t)m * pstride + og + c] * bnf[(int64_t)m * ch + c].y;
         float c1 = bn_train ? (float)(s1 / count) : 0.f;
         float c2 = bn_train ? (float)(s2 / count) : 0.f;
@@ -144,14 +152,15 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ part, int rows_
 }
 
 int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
-                           double count, const float *params, const float4 *bnf, float4 *bnb,
+                           double count, const double *sums, const float *params, const float4 *bnf, float4 *bnb,
                            float *grads, cudaStream_t st) {
     int ch;
     int64_t og, ob;
     if (layer == 1) { ch = d.F1; og = d.og1; ob = d.ob1; }
     else if (layer == 2) { ch = d.G; og = d.og2; ob = d.ob2; }
     else { ch = d.F2; og = d.og3; ob = d.ob3; }
-    bn_bwd_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, params, d.pstride, og,
+    bn_bwd_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, sums,
+                                                         sums != nullptr ? 1.0 / d.dp_world : 1.0, params, d.pstride, og,
                                                          ob, bnf, d.bn_train, bnb, grads);
     EAV_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
     return 0;

@@ -151,8 +151,33 @@ int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, c
 // part: [M][rows_per_model][ch][2] fp32 partial (sum, sum of squares); one warp per
 // (channel, model) reduces them in fp64 in a fixed order.
 // =================================================================================
+__global__ void bn_reduce_kernel(const float *__restrict__ part, int rows_per_model, int ch,
+                                 double *__restrict__ sums) {
+    const int c = blockIdx.x, m = blockIdx.y, lane = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
+    for (int r = lane; r < rows_per_model; r += 32) {
+        s += (double)p[((int64_t)r * ch + c) * 2];
+        q += (double)p[((int64_t)r * ch + c) * 2 + 1];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) { sums[((int64_t)m * ch + c) * 2] = s; sums[((int64_t)m * ch + c) * 2 + 1] = q; }
+}
+
+static int layer_channels(const NetDims &d, int layer) { return layer == 1 ? d.F1 : layer == 2 ? d.G : d.F2; }
+
+int launch_bn_reduce(const NetDims &d, int layer, const float *part, int rows_per_model, double *sums,
+                     cudaStream_t st) {
+    const int ch = layer_channels(d, layer);
+    bn_reduce_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, sums);
+    EAV_CUDA_LAUNCH_CHECK("bn_reduce");
+    return 0;
+}
+
 __global__ void bn_finalize_kernel(const float *__restrict__ part, int rows_per_model, int ch,
-                                   double count, const float *__restrict__ params, int64_t pstride,
+                                   double count, const double *__restrict__ sums,
+                                   const float *__restrict__ params, int64_t pstride,
                                    int64_t og, int64_t ob, float *__restrict__ bn_state,
                                    int64_t bnstride, int64_t orm, int64_t orv, int bn_train,
                                    float eps, float momentum, float4 *__restrict__ stats) {
@@ -162,13 +187,18 @@ __global__ void bn_finalize_kernel(const float *__restrict__ part, int rows_per_
     float mean, var;
     if (bn_train) {
         double s = 0.0, q = 0.0;
-        const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
-        for (int r = lane; r < rows_per_model; r += 32) {
-            s += (double)p[((int64_t)r * ch + c) * 2];
-            q += (double)p[((int64_t)r * ch + c) * 2 + 1];
+        if (sums != nullptr) {          // already reduced (and all-reduced across replicas)
+            s = sums[((int64_t)m * ch + c) * 2];
+            q = sums[((int64_t)m * ch + c) * 2 + 1];
+        } else {
+            const float *p = part + ((int64_t)m * rows_per_model) * ch * 2;
+            for (int r = lane; r < rows_per_model; r += 32) {
+                s += (double)p[((int64_t)r * ch + c) * 2];
+                q += (double)p[((int64_t)r * ch + c) * 2 + 1];
+            }
+            s = warp_sum(s);
+            q = warp_sum(q);
         }
-        s = warp_sum(s);
-        q = warp_sum(q);
         double mu = s / count;
         double vb = q / count - mu * mu;
         if (vb < 0.0) vb = 0.0;
@@ -193,14 +223,14 @@ __global__ void bn_finalize_kernel(const float *__restrict__ part, int rows_per_
 }
 
 int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
-                       double count, const float *params, float *bn_state, float4 *stats,
+                       double count, const double *sums, const float *params, float *bn_state, float4 *stats,
                        cudaStream_t st) {
     int ch;
     int64_t og, ob, orm, orv;
     if (layer == 1) { ch = d.F1; og = d.og1; ob = d.ob1; orm = d.orm1; orv = d.orv1; }
     else if (layer == 2) { ch = d.G; og = d.og2; ob = d.ob2; orm = d.orm2; orv = d.orv2; }
     else { ch = d.F2; og = d.og3; ob = d.ob3; orm = d.orm3; orv = d.orv3; }
-    bn_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, params, d.pstride,
+    bn_finalize_kernel<<<dim3(ch, d.M), 32, 0, st>>>(part, rows_per_model, ch, count, sums, params, d.pstride,
                                                      og, ob, bn_state, d.bnstride, orm, orv, d.bn_train,
                                                      d.eps, d.momentum, stats);
     EAV_CUDA_LAUNCH_CHECK("bn_finalize");

@@ -11,8 +11,11 @@ int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, c
                      float *y1, float *part, int *part_rows, cudaStream_t st);
 // M2/M5/M7 statistics: partial sums -> {mean, invstd, scale, shift}; running-stat update
 int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
-                       double count, const float *params, float *bn_state, float4 *stats,
+                       double count, const double *sums, const float *params, float *bn_state, float4 *stats,
                        cudaStream_t st);
+// partial rows -> per-(model, channel) float64 sums (the buffer a data-parallel run all-reduces)
+int launch_bn_reduce(const NetDims &d, int layer, const float *part, int rows_per_model, double *sums,
+                     cudaStream_t st);
 // M2+M3+M4: BN1 (+ELU) + depthwise spatial conv -> y2 raw [N][G][T] (+ BN2 partial sums)
 int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
                   float *y2, float *part, int *part_rows, cudaStream_t st);
@@ -36,7 +39,7 @@ int launch_tail_bwd(const NetDims &d, const float *dout, const float *probs, con
                     float *dz3, float *part, cudaStream_t st);
 int launch_dense_bwd_w(const NetDims &d, const float *feat, const float *dz, float *grads, cudaStream_t st);
 int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
-                           double count, const float *params, const float4 *bnf, float4 *bnb,
+                           double count, const double *sums, const float *params, const float4 *bnf, float4 *bnb,
                            float *grads, cudaStream_t st);
 int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
                           const float4 *bnb3, const float *params, float *dd1, cudaStream_t st);

@@ -84,14 +84,14 @@ int launch_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_st
 // =================================================================================
 __global__ void __launch_bounds__(256)
 ce_loss_kernel(const float *__restrict__ out, const int64_t *__restrict__ targets,
-               const int32_t *__restrict__ x_index, int B, int NC, float *__restrict__ loss,
+               const int32_t *__restrict__ x_index, int B, int NC, int dp_world, float *__restrict__ loss,
                float *__restrict__ dout, int32_t *__restrict__ n_correct) {
     __shared__ double red[256];
     __shared__ int redc[256];
     const int m = blockIdx.x, tid = threadIdx.x;
     double acc = 0.0;
     int corr = 0;
-    const float invB = 1.f / (float)B;
+    const float invB = 1.f / ((float)B * (float)dp_world);   // mean over the GLOBAL batch
     for (int b = tid; b < B; b += blockDim.x) {
         const int64_t n = (int64_t)m * B + b;
         const int64_t row = x_index ? (int64_t)x_index[n] : n;
@@ -118,7 +118,7 @@ ce_loss_kernel(const float *__restrict__ out, const int64_t *__restrict__ target
         __syncthreads();
     }
     if (tid == 0) {
-        loss[m] = (float)(red[0] / (double)B);
+        loss[m] = (float)(red[0] / ((double)B * dp_world));   // dp: the replicas' values sum to the global mean
         if (n_correct) n_correct[m] = redc[0];
     }
 }
@@ -192,6 +192,7 @@ extern "C" int eav_eegnet_loss(const eav_eegnet_cfg *cfg, const float *out, cons
     EAV_REQUIRE(cfg && out && targets && loss, EAV_ERR_BAD_ARG, "eegnet_loss: null pointer");
     EAV_REQUIRE(cfg->n_models > 0 && cfg->batch > 0 && cfg->n_classes > 0, EAV_ERR_BAD_ARG, "eegnet_loss: bad sizes");
     ce_loss_kernel<<<cfg->n_models, 256, 0, (cudaStream_t)stream>>>(out, targets, x_index, cfg->batch, cfg->n_classes,
+                                                                    cfg->dp_world > 1 ? cfg->dp_world : 1,
                                                                     loss, dout, n_correct);
     EAV_CUDA_LAUNCH_CHECK("eegnet_loss");
     return 0;

@@ -64,7 +64,7 @@ class EegnetDims:
         return 2 * (self.F1 + self.F1 * self.D + self.F2)
 
     def cfg(self, n_models=1, batch=1, bn_train=False, dropout_mode=EAV_DROPOUT_NONE, param_stride=None,
-            bn_stride=None, seed=0, step=0, step_ptr=0) -> EegnetCfg:
+            bn_stride=None, seed=0, step=0, step_ptr=0, dp_world=1) -> EegnetCfg:
         c = EegnetCfg()
         c.n_models, c.batch = n_models, batch
         c.chans, c.samples, c.kern_len = self.Chans, self.Samples, self.kernLength
@@ -74,6 +74,7 @@ class EegnetDims:
         c.dropout_p, c.bn_eps, c.bn_momentum = self.dropoutRate, self.bn_eps, self.bn_momentum
         c.norm_rate = self.norm_rate if self.variant == EAV_VARIANT_TOR else 0.0
         c.seed, c.step, c.step_device_ptr = seed, step, step_ptr
+        c.dp_world = dp_world
         c.param_stride = param_stride if param_stride is not None else 2 ** 31 - 1
         c.bn_stride = bn_stride if bn_stride is not None else 2 ** 31 - 1
         return c

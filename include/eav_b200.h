@@ -123,6 +123,10 @@ typedef struct eav_eegnet_cfg {
     uint64_t step_device_ptr; /* if non-zero: device address of an int64 step counter that
                               replaces `step` (read at kernel run time, so a captured CUDA
                               graph can be replayed with a fresh dropout stream)            */
+    int32_t dp_world;      /* data-parallel replicas sharing ONE model (large-batch mode, config 5):
+                              `batch` is the per-rank share of a global batch of batch*dp_world.
+                              0 or 1 = single device.  See eav_eegnet_stage_allreduce().         */
+    int32_t reserved;
 } eav_eegnet_cfg;
 
 /* Number of parameters of one model and the offsets (in floats) of its tensors inside
@@ -194,6 +198,18 @@ int eav_eegnet_run_stage(const eav_eegnet_cfg *cfg, int stage, const float *x, c
                          float *params, float *bn_state, const uint8_t *mask1, const uint8_t *mask2,
                          float *out, const float *dout, float *grads, void *workspace,
                          size_t workspace_bytes, void *stream);
+
+/*
+ * Large-batch data-parallel mode (dp_world > 1, BASELINE.json configs[4]): the caller drives
+ * the stages one by one and, after a stage for which this returns n_doubles > 0, all-reduces
+ * (sum, e.g. ncclAllReduce over NVLink) the n_doubles float64 values at workspace+offset_bytes
+ * across the replicas before launching the next stage.  These are the BatchNorm statistics
+ * (forward: sum, sum of squares; backward: sum dz, sum dz*xhat) that make train-mode BN equal to
+ * the single-device result at the GLOBAL batch; eval-mode BN needs none.  The flat gradient
+ * arena is all-reduced by the caller after the last stage (gradients are already scaled by
+ * 1/(batch*dp_world) through eav_eegnet_loss).
+ */
+int eav_eegnet_stage_allreduce(const eav_eegnet_cfg *cfg, int stage, size_t *offset_bytes, size_t *n_doubles);
 
 /*
  * torch.optim.Adam step (EEGNet_tor.py:82,110; betas/eps/no weight decay as there)
