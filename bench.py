@@ -108,6 +108,10 @@ def cpu_train_baseline(steps, warmup, bn_train=True):
     import torch
     import eegnet_oracle as EO
     from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
+    try:        # every host core this process may use (torchrun pins OMP_NUM_THREADS=1 otherwise)
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     torch.manual_seed(1)
     sd = EEGNet_tor(5).state_dict()
     params, buffers = EO.split_state(sd, "tor")
