@@ -94,9 +94,9 @@ WsLayout make_ws_layout(const NetDims &d) {
     }
     // BN partial sums (largest user)
     size_t pa = 0;
-    pa = max_sz(pa, N * cdiv(d.C, 4) * cdiv(d.T, 512) * 2 * d.F1);        // tconv_fwd
+    pa = max_sz(pa, N * tconv_fwd_rows_per_sample(d) * 2 * d.F1);         // tconv_fwd
     pa = max_sz(pa, N * cdiv(d.T, 128) * 2 * d.G);                        // dw_fwd
-    pa = max_sz(pa, (size_t)d.M * cdiv(d.B, 2) * cdiv(d.T4, 128) * 2 * d.F2);  // sepconv_fwd
+    pa = max_sz(pa, (size_t)d.M * d.B * cdiv(d.T4, 128) * 2 * d.F2);       // sepconv_fwd (<= one row per sample and tile)
     pa = max_sz(pa, N * 2 * d.F2);                                        // pw_fwd / tail_bwd
     pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
     pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
@@ -183,14 +183,14 @@ extern "C" int eav_eegnet_workspace_offsets(const eav_eegnet_cfg *cfg, size_t *o
 enum {
     ST_TCONV_FWD = 0, ST_BN1_REDUCE, ST_BN1, ST_DW_FWD, ST_RENORM_W2, ST_BN2_REDUCE, ST_BN2, ST_POOL1_FWD,
     ST_SEPCONV_FWD, ST_BN3_REDUCE, ST_BN3, ST_TAIL_FWD, ST_RENORM_WD,
-    ST_TAIL_BWD, ST_DENSE_BWD_W, ST_BN3_BWD_REDUCE, ST_BN3_BWD, ST_SEPCONV_BWD_DX, ST_SEPCONV_BWD_DW, ST_POOL1_BWD,
+    ST_TAIL_BWD, ST_DENSE_BWD_W, ST_BN3_BWD_REDUCE, ST_BN3_BWD, ST_BN3_BWD_APPLY, ST_SEPCONV_BWD_DX, ST_SEPCONV_BWD_DW, ST_POOL1_BWD,
     ST_BN2_BWD_REDUCE, ST_BN2_BWD, ST_DW_BWD, ST_BN1_BWD_REDUCE, ST_BN1_BWD, ST_TCONV_BWD_DW, ST_COUNT
 };
 static const int ST_FWD_END = ST_TAIL_BWD;
 static const char *kStageNames[ST_COUNT] = {
     "tconv_fwd", "bn1_reduce", "bn1_finalize", "dw_fwd", "renorm_depthwise", "bn2_reduce", "bn2_finalize",
     "pool1_fwd", "sepconv_fwd", "bn3_reduce", "bn3_finalize", "tail_fwd", "renorm_dense",
-    "tail_bwd", "dense_bwd_w", "bn3_bwd_reduce", "bn3_bwd_finalize", "sepconv_bwd_dx", "sepconv_bwd_dw",
+    "tail_bwd", "dense_bwd_w", "bn3_bwd_reduce", "bn3_bwd_finalize", "bn3_bwd_apply", "sepconv_bwd_dx", "sepconv_bwd_dw",
     "pool1_bwd", "bn2_bwd_reduce", "bn2_bwd_finalize", "dw_bwd", "bn1_bwd_reduce", "bn1_bwd_finalize",
     "tconv_bwd_dw"};
 
@@ -219,9 +219,9 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     float *partw = WS(float, w.partw), *partw2 = WS(float, w.partw2), *partw3 = WS(float, w.partw3);
     const bool tor = d.variant == EAV_VARIANT_TOR;
     // rows of BatchNorm partial sums each producer writes per model
-    const int rows1 = d.B * cdiv(d.C, 4) * cdiv(d.T, 512);
+    const int rows1 = d.B * tconv_fwd_rows_per_sample(d);
     const int rows2 = d.B * dw_fwd_tiles(d);
-    const int rows3 = tor ? cdiv(d.B, 2) * cdiv(d.T4, 128) : d.B;
+    const int rows3 = tor ? sepconv_fwd_rows_per_model(d) : d.B;
     // data-parallel (dp_world > 1) train-mode BN: statistics go through float64 sums that the
     // caller all-reduces between the *_reduce stage and the *_finalize stage
     const bool dp_bn = d.dp_world > 1 && d.bn_train;
@@ -264,6 +264,9 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_DENSE_BWD_W: return launch_dense_bwd_w(d, WS(float, w.feat), WS(float, w.dz), a.grads, st);
         case ST_BN3_BWD:
             return launch_bn_bwd_finalize(d, 3, part, d.B, W * d.B * d.T4, dp_bn ? sums(3, true) : nullptr, a.params, WS(float4, w.bnf3), WS(float4, w.bnb3), a.grads, st);
+        case ST_BN3_BWD_APPLY:   // dz3 -> dy3 in place (variant 0; variant 1's pointwise kernel applies it itself)
+            if (tor) return launch_bn_bwd_apply(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), st);
+            return 0;
         case ST_SEPCONV_BWD_DX:
             if (tor)
                 return launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
@@ -386,7 +389,7 @@ extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, co
     for (int s = ST_FWD_END; s < ST_COUNT; ++s) {
         if (side != nullptr && (s == ST_DENSE_BWD_W || s == ST_SEPCONV_BWD_DW)) continue;   // issued on the fork
         TRY(run_stage(d, w, s, a, st));
-        if (side != nullptr && (s == ST_TAIL_BWD || s == ST_BN3_BWD)) {
+        if (side != nullptr && (s == ST_TAIL_BWD || s == ST_BN3_BWD_APPLY)) {
             cudaEventRecord(side->fork, st);
             cudaStreamWaitEvent(side->stream, side->fork, 0);
             TRY(run_stage(d, w, s == ST_TAIL_BWD ? ST_DENSE_BWD_W : ST_SEPCONV_BWD_DW, a, side->stream));

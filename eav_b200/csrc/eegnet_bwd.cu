@@ -176,19 +176,43 @@ constexpr int SW_GC = 16;       // input channels per CTA
 constexpr int SW_UP = 128;      // padded positions (T4 <= 128 per pass)
 constexpr int SW_XS = 148;      // d1 row: 7 left pad + 128 + right pad (>= 128+15+4)
 
+__device__ __forceinline__ void cp_async4_ca(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// dy3 (the gradient w.r.t. the conv OUTPUT, BatchNorm-3 backward already applied by
+// bn_bwd_apply) and d1 of sample b+1 stream into the second half of a double buffer with
+// cp.async while sample b feeds the FFMA loop.
 __global__ void __launch_bounds__(256, 2)
-sepconv_bwd_dw_kernel(const float *__restrict__ dz3, const float *__restrict__ y3,
-                      const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
-                      const float *__restrict__ d1, int B, int F2, int G, int L, int padl, int splits,
-                      float *__restrict__ part) {
+sepconv_bwd_dw_kernel(const float *__restrict__ dy3, const float *__restrict__ d1, int B, int F2, int G, int L,
+                      int padl, int splits, float *__restrict__ part) {
     extern __shared__ __align__(16) float smem[];
-    float *dys = smem;                 // [F2][SW_UP]
-    float *xs = smem + F2 * SW_UP;     // [SW_GC][SW_XS]
+    const int stage_floats = F2 * SW_UP + SW_GC * SW_XS;
     const int m = blockIdx.z, split = blockIdx.y, g0 = blockIdx.x * SW_GC;
     const int tid = threadIdx.x;
     const int kq = tid & 1, gl = (tid >> 1) & (SW_GC - 1), og = tid >> 5;  // og: group of 8 output channels
     const int b_lo = (int)((int64_t)B * split / splits), b_hi = (int)((int64_t)B * (split + 1) / splits);
     const int n_og = F2 / 8;  // output-channel groups; threads with og >= n_og idle (F2 <= 64)
+    const int n_ub = (L + SW_UP - 1) / SW_UP;
+
+    auto stage = [&](int step, float *buf) {          // step = (b - b_lo) * n_ub + u-block
+        const int b = b_lo + step / n_ub, u_base = (step % n_ub) * SW_UP;
+        const int64_t n = (int64_t)m * B + b;
+        float *dys = buf, *xs = buf + F2 * SW_UP;
+        for (int i = tid; i < F2 * SW_UP; i += 256) {
+            const int o = i / SW_UP, j = i - o * SW_UP;
+            const int u = u_base + j;
+            if (u < L) cp_async4_ca(dys + i, dy3 + (n * F2 + o) * (int64_t)L + u);
+            else dys[i] = 0.f;
+        }
+        for (int i = tid; i < SW_GC * SW_XS; i += 256) {
+            const int gg = i / SW_XS, j = i - gg * SW_XS;
+            const int u = u_base - padl + j;
+            if (g0 + gg < G && u >= 0 && u < L) cp_async4_ca(xs + i, d1 + (n * G + g0 + gg) * (int64_t)L + u);
+            else xs[i] = 0.f;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
 
     float acc[8][8];
 #pragma unroll
@@ -196,56 +220,33 @@ sepconv_bwd_dw_kernel(const float *__restrict__ dz3, const float *__restrict__ y
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) acc[oo][kk] = 0.f;
 
-    for (int b = b_lo; b < b_hi; ++b) {
-        const int64_t n = (int64_t)m * B + b;
-        for (int u_base = 0; u_base < L; u_base += SW_UP) {
-            __syncthreads();
-            for (int i = tid; i < F2 * SW_UP; i += 256) {
-                int o = i / SW_UP, j = i - o * SW_UP;
-                int u = u_base + j;
-                float v = 0.f;
-                if (u < L) {
-                    int64_t idx = (n * F2 + o) * (int64_t)L + u;
-                    v = dz3[idx];
-                    const float4 kb = bnb[(int64_t)m * F2 + o];
-                    if (bn_train) {
-                        const float4 kf = bnf[(int64_t)m * F2 + o];
-                        v = kb.x * (v - kb.y - (y3[idx] - kf.x) * kf.y * kb.z);
-                    } else {
-                        v = kb.x * v;
-                    }
-                }
-                dys[i] = v;
-            }
-            for (int i = tid; i < SW_GC * SW_XS; i += 256) {
-                int gg = i / SW_XS, j = i - gg * SW_XS;
-                int u = u_base - padl + j;
-                float v = 0.f;
-                if (g0 + gg < G && u >= 0 && u < L) v = d1[(n * G + g0 + gg) * (int64_t)L + u];
-                xs[i] = v;
-            }
-            __syncthreads();
-            if (og < n_og) {
-                const float *dr = dys + og * 8 * SW_UP;
-                const float *xr = xs + gl * SW_XS + 8 * kq;
+    const int n_steps = (b_hi - b_lo) * n_ub;
+    if (n_steps > 0) stage(0, smem);
+    for (int step = 0; step < n_steps; ++step) {
+        float *buf = smem + (step & 1) * stage_floats;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                               // tile `step` visible; the other buffer is free
+        if (step + 1 < n_steps) stage(step + 1, smem + ((step + 1) & 1) * stage_floats);
+        if (og < n_og) {
+            const float *dr = buf + og * 8 * SW_UP;
+            const float *xr = buf + F2 * SW_UP + gl * SW_XS + 8 * kq;
 #pragma unroll 2
-                for (int u = 0; u < SW_UP; u += 4) {
-                    float xw[12];
+            for (int u = 0; u < SW_UP; u += 4) {
+                float xw[12];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        float4 v = *reinterpret_cast<const float4 *>(xr + u + 4 * q);
-                        xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
-                    }
+                for (int q = 0; q < 3; ++q) {
+                    float4 v = *reinterpret_cast<const float4 *>(xr + u + 4 * q);
+                    xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+                }
 #pragma unroll
-                    for (int oo = 0; oo < 8; ++oo) {
-                        float4 d4 = *reinterpret_cast<const float4 *>(dr + oo * SW_UP + u);
-                        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+                for (int oo = 0; oo < 8; ++oo) {
+                    float4 d4 = *reinterpret_cast<const float4 *>(dr + oo * SW_UP + u);
+                    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-                        for (int uu = 0; uu < 4; ++uu)
+                    for (int uu = 0; uu < 4; ++uu)
 #pragma unroll
-                            for (int kk = 0; kk < 8; ++kk)
-                                acc[oo][kk] = fmaf(dv[uu], xw[uu + kk], acc[oo][kk]);
-                    }
+                        for (int kk = 0; kk < 8; ++kk)
+                            acc[oo][kk] = fmaf(dv[uu], xw[uu + kk], acc[oo][kk]);
                 }
             }
         }
@@ -262,14 +263,47 @@ sepconv_bwd_dw_kernel(const float *__restrict__ dz3, const float *__restrict__ y
     }
 }
 
+// In place: dz (gradient w.r.t. the BatchNorm OUTPUT) -> gradient w.r.t. the BatchNorm INPUT,
+//   dy = k * (dz - c1 - xhat * c2)   (c1 = c2 = 0 in eval mode).  Tiny (43 MB at 1344 samples); it lets
+// the two block-2 conv gradient kernels stage their operand with plain asynchronous copies.
+__global__ void bn_bwd_apply_kernel(float *__restrict__ dz, const float *__restrict__ y,
+                                    const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
+                                    int B, int ch, int L, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t nc = i / L;
+        const int c = (int)(nc % ch), n = (int)(nc / ch);
+        const float4 kb = bnb[(int64_t)(n / B) * ch + c];
+        float v = dz[i];
+        if (bn_train) {
+            const float4 kf = bnf[(int64_t)(n / B) * ch + c];
+            v = kb.x * (v - kb.y - (y[i] - kf.x) * kf.y * kb.z);
+        } else {
+            v = kb.x * v;
+        }
+        dz[i] = v;
+    }
+}
+
+int launch_bn_bwd_apply(const NetDims &d, float *dz3, const float *y3, const float4 *bnf3, const float4 *bnb3,
+                        cudaStream_t st) {
+    const int64_t total = (int64_t)d.N * d.F2 * d.T4;
+    int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
+    bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, d.B, d.F2, d.T4, total);
+    EAV_CUDA_LAUNCH_CHECK("bn_bwd_apply");
+    return 0;
+}
+
 int sepconv_dw_splits(const NetDims &d) {
-    // aim for >= ~4 waves of CTAs on 148 SMs x 2 resident, never more splits than samples
-    int per_model = cdiv(d.G, SW_GC);
-    int want = cdiv(148 * 2 * 3, d.M * per_model);
-    int s = want < 1 ? 1 : want;
-    if (s > d.B) s = d.B;
-    if (s > 64) s = 64;
-    return s;
+    // Split the batch into `s` groups: CTAs = M * ceil(G/16) * s, each walking ceil(B/s) samples.
+    const int per_model = cdiv(d.G, SW_GC);
+    const int slots = 148 * 2;
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("EAV_SEPDW_SPLITS"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) return forced < d.B ? forced : d.B;
+    // >= ~4 waves of CTAs (measured on B200: 8 splits 0.643 ms, 4: 0.651, 6: 0.665, 2: 0.81 at M=42, B=32)
+    int s = 1;
+    while (s < d.B && (int64_t)d.M * per_model * s < 4 * slots) s *= 2;
+    return s < d.B ? s : d.B;
 }
 
 int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
@@ -277,10 +311,15 @@ int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, c
     EAV_REQUIRE(d.F2 % 8 == 0 && d.F2 <= 64, EAV_ERR_UNSUPPORTED, "sepconv_dw: F2=%d unsupported (multiple of 8, <= 64)", d.F2);
     EAV_REQUIRE(d.K2 == 16, EAV_ERR_UNSUPPORTED, "sepconv_dw: kernel length %d unsupported", d.K2);
     const int splits = sepconv_dw_splits(d);
-    size_t smem = (size_t)(d.F2 * SW_UP + SW_GC * SW_XS) * sizeof(float);
+    size_t smem = (size_t)2 * (d.F2 * SW_UP + SW_GC * SW_XS) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sepconv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
     dim3 grid(cdiv(d.G, SW_GC), splits, d.M);
-    sepconv_bwd_dw_kernel<<<grid, 256, smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, d1, d.B, d.F2, d.G, d.T4,
-                                                   d.pad2l, splits, part);
+    (void)y3; (void)bnf3; (void)bnb3;      // dz3 already holds dy3 (bn_bwd_apply stage)
+    sepconv_bwd_dw_kernel<<<grid, 256, smem, st>>>(dz3, d1, d.B, d.F2, d.G, d.T4, d.pad2l, splits, part);
     EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dw");
     return launch_reduce_partials(part, splits, (int64_t)d.F2 * d.G * 16, d.M, d.pstride, grads + d.oW3, st);
 }

@@ -14,136 +14,209 @@ namespace eav {
 // the x window, 8 broadcast LDS.128 for the weights and 256 FFMA (95.9 % FFMA issue).
 // Algorithmic work: 2*K1*F1 flop per output sample -> 72.0 MFLOP per EEG epoch.
 // =================================================================================
-constexpr int TC_ROWS = 4;      // channel rows per CTA
 constexpr int TC_R = 8;         // outputs per thread
 constexpr int TC_TPR = 64;      // threads per row
-constexpr int TC_TT = TC_R * TC_TPR;  // 512 time outputs per CTA tile
+constexpr int TC_TT = TC_R * TC_TPR;  // 512 time outputs per item
 
-template <int F1>
-__global__ void __launch_bounds__(TC_ROWS *TC_TPR, 2)
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs: the grid is sized to the resident capacity of the GPU and every CTA walks a
+// CONTIGUOUS range of work items (item = sample n, 3-row channel group, 512-sample time tile),
+// so there is no wave-quantisation tail and the filter bank is re-staged only when the model
+// changes.  The x tile of the NEXT item is fetched with cp.async into the other half of a
+// double buffer while the FFMA loop of the current item runs.
+template <int F1, int TC_ROWS, int KU, int MINB>
+__global__ void __launch_bounds__(TC_ROWS * TC_TPR, MINB)
 tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
                  const float *__restrict__ params, int64_t pstride, int64_t oW1, int B, int C,
-                 int T, int K1, int padl, float *__restrict__ y1, float *__restrict__ part) {
+                 int T, int K1, int padl, int n_items, int groups, int tiles, float *__restrict__ y1,
+                 float *__restrict__ part) {
     extern __shared__ __align__(16) float smem[];
-    const int K1p = (K1 + 3) & ~3;
+    constexpr int TC_THREADS = TC_ROWS * TC_TPR;
+    const int K1p = (K1 + KU - 1) / KU * KU;
     const int XS = TC_TT + K1p + 4;  // multiple of 4
     float *ws = smem;                // [K1p][F1]
-    float *xs = smem + K1p * F1;     // [TC_ROWS][XS]
-
-    const int n = blockIdx.z, m = n / B;
-    const int c0 = blockIdx.y * TC_ROWS;
-    const int tile0 = blockIdx.x * TC_TT;
+    float *xs0 = smem + K1p * F1;    // 2 x [TC_ROWS][XS]
+    __shared__ float red[TC_THREADS / 32][2 * F1];
     const int tid = threadIdx.x;
-    const int64_t xrow = x_index ? (int64_t)x_index[n] : (int64_t)n;
+    const int it_lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
+    const int it_hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
 
-    const float *W1 = params + (int64_t)m * pstride + oW1;
-    for (int i = tid; i < K1p * F1; i += blockDim.x) {
-        int k = i / F1, f = i - k * F1;
-        ws[i] = (k < K1) ? W1[f * K1 + k] : 0.f;
-    }
-    for (int i = tid; i < TC_ROWS * XS; i += blockDim.x) {
-        int r = i / XS, j = i - r * XS;
-        int c = c0 + r, t = tile0 - padl + j;
-        float v = 0.f;
-        if (c < C && t >= 0 && t < T) v = x[(xrow * C + c) * (int64_t)T + t];
-        xs[i] = v;
-    }
-    __syncthreads();
-
-    const int r = tid / TC_TPR, j = tid - r * TC_TPR;
-    const int t0 = j * TC_R;
-    const float *xr = xs + r * XS + t0;
-    float acc[F1][TC_R];
-#pragma unroll
-    for (int f = 0; f < F1; ++f)
-#pragma unroll
-        for (int q = 0; q < TC_R; ++q) acc[f][q] = 0.f;
-
-    for (int k0 = 0; k0 < K1p; k0 += 4) {
-        float xw[TC_R + 4];
-#pragma unroll
-        for (int q = 0; q < (TC_R + 4) / 4; ++q) {
-            float4 v = *reinterpret_cast<const float4 *>(xr + k0 + 4 * q);
-            xw[4 * q + 0] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            float w[F1];
-#pragma unroll
-            for (int q = 0; q < F1 / 4; ++q) {
-                float4 v = *reinterpret_cast<const float4 *>(ws + (k0 + kk) * F1 + 4 * q);
-                w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-            }
-#pragma unroll
-            for (int f = 0; f < F1; ++f)
-#pragma unroll
-                for (int q = 0; q < TC_R; ++q) acc[f][q] = fmaf(w[f], xw[kk + q], acc[f][q]);
-        }
-    }
-
-    const int c = c0 + r;
-    const int tg = tile0 + t0;
-    const bool row_ok = c < C;
-    if (row_ok) {
-#pragma unroll
-        for (int f = 0; f < F1; ++f) {
-            float *dst = y1 + (((int64_t)n * F1 + f) * C + c) * (int64_t)T + tg;
-            if ((T & 3) == 0 && tg + TC_R <= T) {
-                reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
-                reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < TC_R; ++q)
-                    if (tg + q < T) dst[q] = acc[f][q];
+    auto decode = [&](int item, int &n, int &c0, int &tile0) {
+        const int per_n = groups * tiles;
+        n = item / per_n;
+        const int rem = item - n * per_n;
+        const int g = rem / tiles;
+        c0 = g * TC_ROWS;
+        tile0 = (rem - g * tiles) * TC_TT;
+    };
+    auto stage = [&](int item, float *xs) {     // asynchronous: returns with the copies in flight
+        int n, c0, tile0;
+        decode(item, n, c0, tile0);
+        const int64_t xrow = x_index ? (int64_t)x_index[n] : (int64_t)n;
+        const int lim = TC_TT + K1p;
+        for (int r = 0; r < TC_ROWS; ++r) {
+            const int c = c0 + r;
+            const float *src = x + (xrow * C + c) * (int64_t)T;
+            float *dst = xs + r * XS;
+            for (int j = tid; j < XS; j += TC_THREADS) {
+                const int t = tile0 - padl + j;
+                if (c < C && j < lim && t >= 0 && t < T) cp_async4(dst + j, src + t);
+                else dst[j] = 0.f;
             }
         }
-    }
-    if (part != nullptr) {
-        // per-CTA partial sums for BatchNorm statistics (deterministic two-stage reduction)
-        __shared__ float red[(TC_ROWS * TC_TPR / 32)][2 * F1];
-        const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-        for (int f = 0; f < F1; ++f) {
-            float s = 0.f, q2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < TC_R; ++q) {
-                float v = (row_ok && tg + q < T) ? acc[f][q] : 0.f;
-                s += v;
-                q2 = fmaf(v, v, q2);
+        cp_async_commit();
+    };
+
+    if (it_lo < it_hi) stage(it_lo, xs0);
+    int cur_m = -1;
+    for (int item = it_lo; item < it_hi; ++item) {
+        float *xs = xs0 + ((item - it_lo) & 1) * (TC_ROWS * XS);
+        int n, c0, tile0;
+        decode(item, n, c0, tile0);
+        const int m = n / B;
+        if (m != cur_m) {                       // (re)stage the filter bank of this model
+            __syncthreads();                    // nobody still reads the previous bank
+            const float *W1 = params + (int64_t)m * pstride + oW1;
+            for (int i = tid; i < K1p * F1; i += TC_THREADS) {
+                int k = i / F1, f = i - k * F1;
+                ws[i] = (k < K1) ? W1[f * K1 + k] : 0.f;
             }
-            s = warp_sum(s);
-            q2 = warp_sum(q2);
-            if (lane == 0) { red[warp][2 * f] = s; red[warp][2 * f + 1] = q2; }
+            cur_m = m;
         }
-        __syncthreads();
-        if (tid < 2 * F1) {
-            float s = 0.f;
+        cp_async_wait<0>();
+        __syncthreads();                        // tile `item` and the weights are visible to all
+        if (item + 1 < it_hi) stage(item + 1, xs0 + ((item + 1 - it_lo) & 1) * (TC_ROWS * XS));
+
+        const int r = tid / TC_TPR, j = tid - r * TC_TPR;
+        const int t0 = j * TC_R;
+        const float *xr = xs + r * XS + t0;
+        float acc[F1][TC_R];
 #pragma unroll
-            for (int w = 0; w < TC_ROWS * TC_TPR / 32; ++w) s += red[w][tid];
-            int64_t row = ((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-            part[row * (2 * F1) + tid] = s;
+        for (int f = 0; f < F1; ++f)
+#pragma unroll
+            for (int q = 0; q < TC_R; ++q) acc[f][q] = 0.f;
+
+        for (int k0 = 0; k0 < K1p; k0 += KU) {
+            float xw[TC_R + KU];
+#pragma unroll
+            for (int q = 0; q < (TC_R + KU) / 4; ++q) {
+                float4 v = *reinterpret_cast<const float4 *>(xr + k0 + 4 * q);
+                xw[4 * q + 0] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int kk = 0; kk < KU; ++kk) {
+                float w[F1];
+#pragma unroll
+                for (int q = 0; q < F1 / 4; ++q) {
+                    float4 v = *reinterpret_cast<const float4 *>(ws + (k0 + kk) * F1 + 4 * q);
+                    w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int f = 0; f < F1; ++f)
+#pragma unroll
+                    for (int q = 0; q < TC_R; ++q) acc[f][q] = fmaf(w[f], xw[kk + q], acc[f][q]);
+            }
+        }
+
+        const int c = c0 + r;
+        const int tg = tile0 + t0;
+        const bool row_ok = c < C;
+        if (row_ok) {
+#pragma unroll
+            for (int f = 0; f < F1; ++f) {
+                float *dst = y1 + (((int64_t)n * F1 + f) * C + c) * (int64_t)T + tg;
+                if ((T & 3) == 0 && tg + TC_R <= T) {
+                    reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
+                    reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < TC_R; ++q)
+                        if (tg + q < T) dst[q] = acc[f][q];
+                }
+            }
+        }
+        if (part != nullptr) {
+            // per-item partial sums for BatchNorm statistics (deterministic two-stage reduction)
+            const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+            for (int f = 0; f < F1; ++f) {
+                float s = 0.f, q2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < TC_R; ++q) {
+                    float v = (row_ok && tg + q < T) ? acc[f][q] : 0.f;
+                    s += v;
+                    q2 = fmaf(v, v, q2);
+                }
+                s = warp_sum(s);
+                q2 = warp_sum(q2);
+                if (lane == 0) { red[warp][2 * f] = s; red[warp][2 * f + 1] = q2; }
+            }
+            __syncthreads();
+            if (tid < 2 * F1) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < TC_THREADS / 32; ++w) s += red[w][tid];
+                part[(int64_t)item * (2 * F1) + tid] = s;      // item-major == model-major rows
+            }
         }
     }
+}
+
+// variant table (EAV_TC_VARIANT env var for A/B runs; default = the fastest measured)
+static int tc_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EAV_TC_VARIANT"); v = e ? atoi(e) : 2; }   // measured on B200: 2 (4 rows, 4 taps/iter) 1.91 ms, 0: 2.02, 1: 2.08, 3: 1.93
+    return v;
+}
+static int tc_rows() { int v = tc_variant(); return (v == 2 || v == 3) ? 4 : 3; }
+static int tc_ku() { int v = tc_variant(); return (v == 1 || v == 3) ? 8 : 4; }
+
+int tconv_fwd_rows_per_sample(const NetDims &d) { return cdiv(d.C, tc_rows()) * cdiv(d.T, TC_TT); }
+
+template <int ROWS, int KU, int MINB>
+static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
+                              float *y1, float *part, int *part_rows, cudaStream_t st) {
+    constexpr int THREADS = ROWS * TC_TPR;
+    const int K1p = (d.K1 + KU - 1) / KU * KU;
+    const int XS = TC_TT + K1p + 4;
+    size_t smem = (size_t)(K1p * d.F1 + 2 * ROWS * XS) * sizeof(float);
+    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_fwd: kernLength %d too large", d.K1);
+    const int groups = cdiv(d.C, ROWS), tiles = cdiv(d.T, TC_TT);
+    const int64_t n_items = (int64_t)d.N * groups * tiles;
+    static int resident = 0;          // CTAs the device holds at once (SMs x occupancy)
+    static size_t resident_smem = 0;
+    if (resident == 0 || resident_smem != smem) {
+        cudaFuncSetAttribute(tconv_fwd_kernel<8, ROWS, KU, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tconv_fwd_kernel<8, ROWS, KU, MINB>, THREADS, smem);
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+        resident_smem = smem;
+    }
+    const int grid = (int)(n_items < resident ? n_items : resident);
+    tconv_fwd_kernel<8, ROWS, KU, MINB><<<grid, THREADS, smem, st>>>(x, x_index, params, d.pstride, d.oW1, d.B, d.C, d.T,
+                                                                    d.K1, d.pad1l, (int)n_items, groups, tiles, y1, part);
+    EAV_CUDA_LAUNCH_CHECK("tconv_fwd");
+    if (part_rows) *part_rows = d.B * groups * tiles;
+    return 0;
 }
 
 int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
                      float *y1, float *part, int *part_rows, cudaStream_t st) {
     EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_fwd: F1=%d unsupported (only 8)", d.F1);
-    const int K1p = (d.K1 + 3) & ~3;
-    const int XS = TC_TT + K1p + 4;
-    size_t smem = (size_t)(K1p * d.F1 + TC_ROWS * XS) * sizeof(float);
-    EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_fwd: kernLength %d too large", d.K1);
-    dim3 grid(cdiv(d.T, TC_TT), cdiv(d.C, TC_ROWS), d.N);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(tconv_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+    switch (tc_variant()) {
+        case 1: return launch_tconv_fwd_v<3, 8, 3>(d, x, x_index, params, y1, part, part_rows, st);
+        case 2: return launch_tconv_fwd_v<4, 4, 2>(d, x, x_index, params, y1, part, part_rows, st);
+        case 3: return launch_tconv_fwd_v<4, 8, 2>(d, x, x_index, params, y1, part, part_rows, st);
+        default: return launch_tconv_fwd_v<3, 4, 3>(d, x, x_index, params, y1, part, part_rows, st);
     }
-    tconv_fwd_kernel<8><<<grid, TC_ROWS * TC_TPR, smem, st>>>(x, x_index, params, d.pstride, d.oW1, d.B,
-                                                            d.C, d.T, d.K1, d.pad1l, y1, part);
-    EAV_CUDA_LAUNCH_CHECK("tconv_fwd");
-    if (part_rows) *part_rows = d.B * grid.y * grid.x;
-    return 0;
 }
 
 // =================================================================================
@@ -398,34 +471,94 @@ constexpr int SC_UT = 128;     // positions per CTA
 constexpr int SC_XS = SC_UT + SC_K;  // 144: padded input row
 constexpr int SC_CO = 64;      // output channels per CTA
 
+__device__ __forceinline__ void cp_async16_cg(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// Work items: `n_pairs` two-sample items first, then single-sample items for what is left, so
+// that the last (partial) wave of CTAs runs half-size items instead of idling the GPU.
+// Weight chunks (4 input channels x 64 outputs x 16 taps = 16 KB) are double-buffered with
+// 16-byte cp.async: chunk i+1 streams in while chunk i feeds the FFMA loop.  In MODE 1 the
+// weights stay unflipped in smem ([o'][g][k] is contiguous in global) and the flip is done by
+// indexing the register window backwards.
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
                const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
                const float *__restrict__ params, int64_t pstride, int64_t oW3, int B, int Cin, int Cout,
-               int L, int padl, float *__restrict__ out, float *__restrict__ part) {
+               int L, int padl, int n_pairs, int pairs_per_model, int singles_per_model,
+               float *__restrict__ out, float *__restrict__ part) {
     extern __shared__ __align__(16) float smem[];
-    float *ws = smem;                            // [SC_GC][SC_CO][SC_K]
-    float *xs = smem + SC_GC * SC_CO * SC_K;     // [SC_SC][Cin][SC_XS]
-    const int pairs = (B + SC_SC - 1) / SC_SC;
-    const int m = blockIdx.z / pairs, pair = blockIdx.z - m * pairs;
+    float *ws0 = smem;                               // 2 x [SC_GC][SC_CO][SC_K]
+    float *xs = smem + 2 * SC_GC * SC_CO * SC_K;     // [SC_SC][Cin][SC_XS]
+    // decode the work item -> (model, first sample, number of samples)
+    int m, b0, ns, part_row;
+    {
+        const int it = blockIdx.z;
+        if (it < n_pairs) {
+            m = it / pairs_per_model;
+            const int p = it - m * pairs_per_model;
+            b0 = p * SC_SC;
+            ns = min(SC_SC, B - b0);
+            part_row = m * (pairs_per_model + singles_per_model) + p;
+        } else {
+            const int j = it - n_pairs;                 // only reached when singles_per_model > 0
+            m = j / max(singles_per_model, 1);
+            const int q = j - m * singles_per_model;
+            b0 = pairs_per_model * SC_SC + q;
+            ns = 1;
+            part_row = m * (pairs_per_model + singles_per_model) + pairs_per_model + q;
+        }
+    }
     const int o_base = blockIdx.y * SC_CO;
     const int u0 = blockIdx.x * SC_UT;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const float *W3 = params + (int64_t)m * pstride + oW3;
+    const bool w_vec = (reinterpret_cast<uintptr_t>(W3) & 15) == 0;    // arena slices are 16-byte aligned
 
+    auto stage_w = [&](int g0, float *ws) {
+        // ws[gl][o][k]
+        if (w_vec) {
+            for (int i = tid; i < SC_GC * SC_CO * (SC_K / 4); i += 256) {
+                const int gl = i / (SC_CO * 4), rem = i - gl * SC_CO * 4;
+                const int o = rem >> 2, k4 = (rem & 3) * 4;
+                const int gi = g0 + gl, oc = o_base + o;
+                float *dst = ws + (gl * SC_CO + o) * SC_K + k4;
+                if (gi < Cin && oc < Cout) {
+                    const float *src = (MODE == 0) ? W3 + ((int64_t)oc * Cin + gi) * SC_K + k4      // W3[o][g][k]
+                                                   : W3 + ((int64_t)gi * Cout + oc) * SC_K + k4;    // W3[o'=gi][g=oc][k]
+                    cp_async16_cg(dst, src);
+                } else {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+            for (int i = tid; i < SC_GC * SC_CO * SC_K; i += 256) {
+                const int gl = i / (SC_CO * SC_K), rem = i - gl * SC_CO * SC_K;
+                const int o = rem / SC_K, k = rem - o * SC_K;
+                const int gi = g0 + gl, oc = o_base + o;
+                float w = 0.f;
+                if (gi < Cin && oc < Cout)
+                    w = (MODE == 0) ? W3[((int64_t)oc * Cin + gi) * SC_K + k] : W3[((int64_t)gi * Cout + oc) * SC_K + k];
+                ws[i] = w;
+            }
+        }
+        cp_async_commit();
+    };
+
+    stage_w(0, ws0);
     // stage the input rows (with the BatchNorm-backward transform in MODE 1)
     for (int i = tid; i < SC_SC * Cin * SC_XS; i += 256) {
         int s = i / (Cin * SC_XS);
         int rem = i - s * Cin * SC_XS;
         int ch = rem / SC_XS, j = rem - ch * SC_XS;
-        int b = pair * SC_SC + s;
+        int b = b0 + s;
         int u = u0 - padl + j;
         float v = 0.f;
-        if (b < B && u >= 0 && u < L) {
+        if (s < ns && u >= 0 && u < L) {
             int64_t idx = (((int64_t)(m * B + b)) * Cin + ch) * (int64_t)L + u;
             v = in[idx];
-            if (MODE == 1) {
+            if (MODE == 1 && bnb != nullptr) {   // (unused since bn_bwd_apply materialises dy3; kept for callers that skip it)
                 const float4 kb = bnb[(int64_t)m * Cin + ch];
                 if (bn_train) {
                     const float4 kf = bnf[(int64_t)m * Cin + ch];
@@ -447,21 +580,12 @@ sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
 #pragma unroll
             for (int uu = 0; uu < 4; ++uu) acc[s][oo][uu] = 0.f;
 
-    for (int g0 = 0; g0 < Cin; g0 += SC_GC) {
-        __syncthreads();
-        for (int i = tid; i < SC_GC * SC_CO * SC_K; i += 256) {
-            int gl = i / (SC_CO * SC_K);
-            int rem = i - gl * SC_CO * SC_K;
-            int o = rem / SC_K, k = rem - o * SC_K;
-            float w = 0.f;
-            int gi = g0 + gl, oc = o_base + o;
-            if (gi < Cin && oc < Cout) {
-                if (MODE == 0) w = W3[((int64_t)oc * Cin + gi) * SC_K + k];            // W3[o][g][k]
-                else           w = W3[((int64_t)gi * Cout + oc) * SC_K + (SC_K - 1 - k)]; // W3[o'=gi][g=oc][15-k]
-            }
-            ws[i] = w;
-        }
-        __syncthreads();
+    int buf = 0;
+    for (int g0 = 0; g0 < Cin; g0 += SC_GC, buf ^= 1) {
+        cp_async_wait<0>();
+        __syncthreads();                               // chunk g0 (and, first time, xs) visible; other buffer free
+        if (g0 + SC_GC < Cin) stage_w(g0 + SC_GC, ws0 + (buf ^ 1) * (SC_GC * SC_CO * SC_K));
+        const float *ws = ws0 + buf * (SC_GC * SC_CO * SC_K);
 #pragma unroll 1
         for (int gl = 0; gl < SC_GC; ++gl) {
             if (g0 + gl >= Cin) break;
@@ -487,8 +611,11 @@ sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
 #pragma unroll
                         for (int s = 0; s < SC_SC; ++s)
 #pragma unroll
-                            for (int uu = 0; uu < 4; ++uu)
-                                acc[s][oo][uu] = fmaf(wv[kk], xw[s][k + kk + uu], acc[s][oo][uu]);
+                            for (int uu = 0; uu < 4; ++uu) {
+                                // MODE 0: in[u + k - padl];  MODE 1 (flipped kernel): in[u - k + (K-1) - padl']
+                                const int wi = (MODE == 0) ? (k + kk + uu) : (SC_K - 1 - (k + kk) + uu);
+                                acc[s][oo][uu] = fmaf(wv[kk], xw[s][wi], acc[s][oo][uu]);
+                            }
                 }
             }
         }
@@ -501,8 +628,8 @@ sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int s = 0; s < SC_SC; ++s) {
-            const int b = pair * SC_SC + s;
-            if (b < B && oc < Cout) {
+            const int b = b0 + s;
+            if (s < ns && oc < Cout) {
                 float *dst = out + (((int64_t)(m * B + b)) * Cout + oc) * (int64_t)L + ub;
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu)
@@ -517,7 +644,7 @@ sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
             s1 = warp_sum(s1);
             s2 = warp_sum(s2);
             if (threadIdx.x == 0 && oc < Cout) {
-                int64_t row = ((int64_t)m * pairs + pair) * gridDim.x + blockIdx.x;
+                int64_t row = (int64_t)part_row * gridDim.x + blockIdx.x;
                 part[(row * Cout + oc) * 2] = s1;
                 part[(row * Cout + oc) * 2 + 1] = s2;
             }
@@ -525,8 +652,35 @@ sepconv_kernel(const float *__restrict__ in, const float *__restrict__ yraw,
     }
 }
 
+// item plan shared by both modes: full waves of two-sample items, the remainder as singles
+struct SepPlan { int pairs_per_model, singles_per_model; };
+static SepPlan sepconv_plan(const NetDims &d, int ctas_xy) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = sms * 2 / (ctas_xy > 0 ? ctas_xy : 1);      // 2 resident CTAs per SM
+    const int pairs_all = d.B / SC_SC;                            // per model, whole pairs only
+    int singles = d.B - pairs_all * SC_SC;                        // odd batch: one single anyway
+    int pairs = pairs_all;
+    const int64_t total_pairs = (int64_t)d.M * pairs_all;
+    static int split_tail = -1;
+    if (split_tail < 0) { const char *e = getenv("EAV_SEP_SPLIT_TAIL"); split_tail = e ? atoi(e) : 0; }   // measured: splitting the tail wave is slower (0.55 vs 0.47 ms)
+    if (split_tail && slots > 0 && total_pairs > slots) {
+        // pairs beyond the last full wave are converted to singles, spread evenly over the models
+        const int64_t tail = total_pairs % slots;
+        int conv = (int)cdiv64(tail, d.M);                        // per model
+        if (conv > pairs) conv = pairs;
+        if (tail > 0 && tail * 2 <= slots) { pairs -= conv; singles += conv * SC_SC; }
+    }
+    return {pairs, singles};
+}
+int sepconv_fwd_rows_per_model(const NetDims &d) {
+    SepPlan p = sepconv_plan(d, cdiv(d.T4, SC_UT) * cdiv(d.F2, SC_CO));
+    return (p.pairs_per_model + p.singles_per_model) * cdiv(d.T4, SC_UT);
+}
+
 static size_t sepconv_smem(int Cin) {
-    return (size_t)(SC_GC * SC_CO * SC_K + SC_SC * Cin * SC_XS) * sizeof(float);
+    return (size_t)(2 * SC_GC * SC_CO * SC_K + SC_SC * Cin * SC_XS) * sizeof(float);
 }
 
 int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *y3,
@@ -539,12 +693,14 @@ int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, f
         cudaFuncSetAttribute(sepconv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const int pairs = cdiv(d.B, SC_SC);
-    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.F2, SC_CO), d.M * pairs);
+    const SepPlan pl = sepconv_plan(d, cdiv(d.T4, SC_UT) * cdiv(d.F2, SC_CO));
+    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.F2, SC_CO), d.M * (pl.pairs_per_model + pl.singles_per_model));
     sepconv_kernel<0><<<grid, dim3(32, 8), smem, st>>>(d1, nullptr, nullptr, nullptr, 0, params, d.pstride,
-                                                       d.oW3, d.B, d.G, d.F2, d.T4, d.pad2l, y3, part);
+                                                       d.oW3, d.B, d.G, d.F2, d.T4, d.pad2l,
+                                                       d.M * pl.pairs_per_model, pl.pairs_per_model,
+                                                       pl.singles_per_model, y3, part);
     EAV_CUDA_LAUNCH_CHECK("sepconv_fwd");
-    if (part_rows) *part_rows = pairs * grid.x;
+    if (part_rows) *part_rows = (pl.pairs_per_model + pl.singles_per_model) * grid.x;
     return 0;
 }
 
@@ -557,11 +713,13 @@ int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, c
         cudaFuncSetAttribute(sepconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    const int pairs = cdiv(d.B, SC_SC);
-    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.G, SC_CO), d.M * pairs);
+    const SepPlan pl = sepconv_plan(d, cdiv(d.T4, SC_UT) * cdiv(d.G, SC_CO));
+    dim3 grid(cdiv(d.T4, SC_UT), cdiv(d.G, SC_CO), d.M * (pl.pairs_per_model + pl.singles_per_model));
     // flipped kernel: left padding K-1-pad2l
-    sepconv_kernel<1><<<grid, dim3(32, 8), smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, params, d.pstride,
-                                                       d.oW3, d.B, d.F2, d.G, d.T4, d.K2 - 1 - d.pad2l, dd1,
+    sepconv_kernel<1><<<grid, dim3(32, 8), smem, st>>>(dz3, y3, bnf3, nullptr, d.bn_train, params, d.pstride,
+                                                       d.oW3, d.B, d.F2, d.G, d.T4, d.K2 - 1 - d.pad2l,
+                                                       d.M * pl.pairs_per_model, pl.pairs_per_model,
+                                                       pl.singles_per_model, dd1,
                                                        nullptr);
     EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dx");
     return 0;

@@ -41,6 +41,8 @@ int launch_dense_bwd_w(const NetDims &d, const float *feat, const float *dz, flo
 int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
                            double count, const double *sums, const float *params, const float4 *bnf, float4 *bnb,
                            float *grads, cudaStream_t st);
+int launch_bn_bwd_apply(const NetDims &d, float *dz3, const float *y3, const float4 *bnf3, const float4 *bnb3,
+                        cudaStream_t st);
 int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
                           const float4 *bnb3, const float *params, float *dd1, cudaStream_t st);
 int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
@@ -59,6 +61,8 @@ int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index
                         const float *y1, const float4 *bnf1, const float4 *bnb1, float *part,
                         float *grads, cudaStream_t st);
 
+int tconv_fwd_rows_per_sample(const NetDims &d);   // BN1 partial rows per sample written by tconv_fwd
+int sepconv_fwd_rows_per_model(const NetDims &d);   // BN3 partial rows per model written by sepconv_fwd
 int dw_fwd_tiles(const NetDims &d);   // time tiles per (sample, filter) of dw_fwd == BN2 partial rows per sample
 
 // ---- small ops -------------------------------------------------------------------

@@ -141,6 +141,34 @@ ffma_peak_kernel(float *out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;   // never true: keeps the loop alive
 }
 
+// Same idea for the instruction mix the convolution kernels actually issue: an 8x8 register
+// outer product acc[i][j] += a[i]*b[j] (three register operands per FFMA, operand-reuse cache and
+// register banks in play).  This is the practical ceiling of a register-blocked fp32 kernel.
+__global__ void __launch_bounds__(256)
+ffma_outer_kernel(float *out, const float *in, int iters) {
+    float a[8], b[8], acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = in[threadIdx.x + 32 * i]; b[i] = in[threadIdx.x + 32 * i + 256]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rot = 0; rot < 8; ++rot)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[(j + rot) & 7], acc[i][j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace eav
 
 using namespace eav;
@@ -195,6 +223,40 @@ extern "C" int eav_eegnet_loss(const eav_eegnet_cfg *cfg, const float *out, cons
                                                                     cfg->dp_world > 1 ? cfg->dp_world : 1,
                                                                     loss, dout, n_correct);
     EAV_CUDA_LAUNCH_CHECK("eegnet_loss");
+    return 0;
+}
+
+extern "C" int eav_measure_fp32_peak_outer(double *tflops, void *stream) {
+    EAV_REQUIRE(tflops, EAV_ERR_BAD_ARG, "measure_fp32_peak_outer: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float *buf = nullptr;
+    if (cudaMalloc(&buf, 4096 * sizeof(float)) != cudaSuccess) { set_error("measure_fp32_peak_outer: cudaMalloc failed"); return (int)cudaErrorMemoryAllocation; }
+    cudaMemsetAsync(buf, 0, 4096 * sizeof(float), st);
+    const int iters = 1024, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 16);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, st);
+        ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 512 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("measure_fp32_peak_outer: %s", cudaGetErrorString(e)); return (int)e; }
+    *tflops = best;
     return 0;
 }
 

