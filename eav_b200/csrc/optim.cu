@@ -169,6 +169,35 @@ ffma_outer_kernel(float *out, const float *in, int iters) {
     if (s == 123.456f) out[0] = s;
 }
 
+// Third form: one operand of every FFMA comes from the constant bank through a uniform
+// register (LDCU -> UR), as the FIR taps do: acc[i][j] += a[i] * c_tab[k][j].
+__constant__ float c_peak_tab[256 * 8];
+__global__ void __launch_bounds__(256)
+ffma_outer_const_kernel(float *out, const float *in, int iters) {
+    float a[8], acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = in[threadIdx.x + 32 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 8
+        for (int k = 0; k < 256; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[(i + k) & 7], c_peak_tab[k * 8 + j], acc[i][j]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace eav
 
 using namespace eav;
@@ -239,16 +268,21 @@ extern "C" int eav_measure_fp32_peak_outer(double *tflops, void *stream) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 16);
+    const bool use_const = getenv("EAV_PEAK_CONST") != nullptr;    // experiment: uniform-register operand form
+    if (use_const) ffma_outer_const_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 1);
+    else ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 16);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, st);
-        ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters);
+        if (use_const) ffma_outer_const_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters / 32);
+        else ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        double tf = 2.0 * 512 * (double)iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        double per_iter = use_const ? 256.0 * 64 : 512.0;
+        double n_it = use_const ? iters / 32 : iters;
+        double tf = 2.0 * per_iter * n_it * 256.0 * blocks / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
     cudaEventDestroy(e0);
