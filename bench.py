@@ -401,6 +401,7 @@ def main():
         tot = sum(stages.values())
         dom = max(("tconv_fwd", "tconv_bwd_dw"), key=lambda k: stages[k])
         peak = ops.measure_fp32_peak()
+        peak_outer = ops.measure_fp32_peak(outer_product=True)
         ach = TCONV_FLOP_PER_SAMPLE * M * B / (stages[dom] * 1e-3) / 1e12
         traffic = None
         try:
@@ -413,6 +414,11 @@ def main():
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s. MEASURED_PEAKS.json holds "
                                "only HBM and bf16-tensor peaks; this kernel runs on the fp32 CUDA cores by design "
                                "(1e-4 parity budget rules out TF32, north_star)",
+                "peak_register_operands": peak_outer,
+                "frac_of_register_operand_peak": ach / peak_outer,
+                "peak_register_operands_note": "same device, 8x8 register outer product (three register operands per "
+                                               "FFMA, the instruction mix of a register-blocked convolution): the "
+                                               "register file, not the FMA pipe, caps this form",
                 "algorithmic_flops_per_launch": TCONV_FLOP_PER_SAMPLE * M * B,
                 "whole_step": {"achieved": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                "frac": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12 / peak}}

@@ -525,13 +525,19 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // The raw conv output y1, dz2 (and y2 in train mode, parked in `red`) are staged with 16-byte
 // cp.async (LDGSTS): every load of the CTA is in flight at once and no register is tied up.
 // a1 = act(BN1(y1)) and act' are recomputed from the staged y1, so y1 is read from HBM once.
+// CT / TT / DT: compile-time Chans / Samples / D (0 = use the runtime value).  The dataset shape
+// (30, 500, 8) gets its own instantiation: with constant trip counts the staging and phase loops
+// unroll and the address arithmetic folds (the generic build spent ~40 % of its issue slots on
+// integer/branch instructions).
+template <int CT, int TT, int DT>
 __global__ void __launch_bounds__(DB_THREADS, 2)
 dw_bwd_kernel(const float *__restrict__ dz2, const float *__restrict__ y2, const float4 *__restrict__ bnf2,
               const float4 *__restrict__ bnb2, const float *__restrict__ y1, const float4 *__restrict__ bnf1,
               const float *__restrict__ params, int64_t pstride, int64_t oW2, int bn_train, int elu1, int B,
-              int F1, int D, int C, int T, float *__restrict__ dz1, float *__restrict__ part_w,
+              int F1, int D_rt, int C_rt, int T_rt, float *__restrict__ dz1, float *__restrict__ part_w,
               float *__restrict__ part_bn) {
     extern __shared__ __align__(16) float smem[];
+    const int C = CT ? CT : C_rt, T = TT ? TT : T_rt, D = DT ? DT : D_rt;
     const int TSa = ((T + 3) & ~3) + 4;
     float *y1s = smem;                    // [C][TSa]   raw conv output, zero padded past T
     float *dys = y1s + C * TSa;           // [8][TSa]   dL/d(depthwise output) (BN2 backward applied), rows >= D zero
@@ -709,12 +715,18 @@ int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const flo
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "dw_bwd: Chans*Samples too large for one CTA");
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dw_bwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(dw_bwd_kernel<30, 500, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    dw_bwd_kernel<<<d.N * d.F1, DB_THREADS, smem, st>>>(dz2, y2, bnf2, bnb2, y1, bnf1, params, d.pstride, d.oW2,
-                                                       d.bn_train, d.variant == EAV_VARIANT_TOR, d.B, d.F1, d.D,
-                                                       d.C, d.T, dz1, part_w, part_bn);
+    if (d.C == 30 && d.T == 500 && d.D == 8)
+        dw_bwd_kernel<30, 500, 8><<<d.N * d.F1, DB_THREADS, smem, st>>>(dz2, y2, bnf2, bnb2, y1, bnf1, params, d.pstride, d.oW2,
+                                                                       d.bn_train, d.variant == EAV_VARIANT_TOR, d.B, d.F1,
+                                                                       d.D, d.C, d.T, dz1, part_w, part_bn);
+    else
+        dw_bwd_kernel<0, 0, 0><<<d.N * d.F1, DB_THREADS, smem, st>>>(dz2, y2, bnf2, bnb2, y1, bnf1, params, d.pstride, d.oW2,
+                                                                    d.bn_train, d.variant == EAV_VARIANT_TOR, d.B, d.F1, d.D,
+                                                                    d.C, d.T, dz1, part_w, part_bn);
     EAV_CUDA_LAUNCH_CHECK("dw_bwd");
     // part_w is [N][G*C]: reduce over the B samples of each model
     return launch_reduce_partials(part_w, d.B, (int64_t)d.G * d.C, d.M, d.pstride, grads + d.oW2, st);

@@ -320,7 +320,7 @@ constexpr int DMAX = 8;
 
 // VEC = 4: each thread owns 4 consecutive time samples (128-bit loads/stores, needs T % 4 == 0);
 // VEC = 1: scalar fallback for any T.
-template <int VEC>
+template <int VEC, int UNR>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, int64_t pstride,
               int64_t oW2, const float4 *__restrict__ bn1, int B, int F1, int D, int C, int T,
@@ -341,27 +341,40 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
         for (int e = 0; e < VEC; ++e) acc[dd][e] = 0.f;
     if (t < T) {
         const float *src = y1 + (((int64_t)n * F1 + f) * C) * (int64_t)T + t;
-#pragma unroll 6
-        for (int c = 0; c < C; ++c) {
-            float a[VEC];
-            if (VEC == 4) {
-                float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)c * T);
-                a[0] = v.x; a[1 % VEC] = v.y; a[2 % VEC] = v.z; a[3 % VEC] = v.w;
-            } else {
-                a[0] = src[(int64_t)c * T];
-            }
+        // UNR electrode rows are fetched back to back (UNR independent 128-bit loads in flight per
+        // thread) before any of them is consumed: the kernel is HBM-latency bound otherwise.
+        for (int c0 = 0; c0 < C; c0 += UNR) {
+            float a[UNR][VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                float v = fmaf(a[e], st.z, st.w);
-                a[e] = elu1 ? elu_f(v) : v;
-            }
-#pragma unroll
-            for (int dd = 0; dd < DMAX; ++dd)
-                if (dd < D) {
-                    const float w = w2s[dd * C + c];
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) acc[dd][e] = fmaf(w, a[e], acc[dd][e]);
+            for (int u = 0; u < UNR; ++u) {
+                const int c = c0 + u;
+                if (c < C) {
+                    if (VEC == 4) {
+                        float4 v = *reinterpret_cast<const float4 *>(src + (int64_t)c * T);
+                        a[u][0] = v.x; a[u][1 % VEC] = v.y; a[u][2 % VEC] = v.z; a[u][3 % VEC] = v.w;
+                    } else {
+                        a[u][0] = src[(int64_t)c * T];
+                    }
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int c = c0 + u;
+                if (c < C) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        float v = fmaf(a[u][e], st.z, st.w);
+                        a[u][e] = elu1 ? elu_f(v) : v;
+                    }
+#pragma unroll
+                    for (int dd = 0; dd < DMAX; ++dd)
+                        if (dd < D) {
+                            const float w = w2s[dd * C + c];
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) acc[dd][e] = fmaf(w, a[u][e], acc[dd][e]);
+                        }
+                }
+            }
         }
 #pragma unroll
         for (int dd = 0; dd < DMAX; ++dd)
@@ -404,10 +417,17 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
     dim3 grid(dw_fwd_tiles(d), d.F1, d.N);
     const size_t smem = (size_t)d.D * d.C * sizeof(float);
     const int elu1 = d.variant == EAV_VARIANT_TOR;
-    if ((d.T & 3) == 0)
-        dw_fwd_kernel<4><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
-    else
-        dw_fwd_kernel<1><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+    static int unr = -1;
+    if (unr < 0) { const char *e = getenv("EAV_DWF_UNR"); unr = e ? atoi(e) : 5; }   // measured on B200: 5 -> 0.195 ms, 3: 0.203, 6: 0.209, 10: 0.256, 15: 0.434
+    if ((d.T & 3) == 0) {
+        if (unr == 3) dw_fwd_kernel<4, 3><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        else if (unr == 6) dw_fwd_kernel<4, 6><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        else if (unr == 15) dw_fwd_kernel<4, 15><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        else if (unr == 10) dw_fwd_kernel<4, 10><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        else dw_fwd_kernel<4, 5><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+    } else {
+        dw_fwd_kernel<1, 8><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+    }
     EAV_CUDA_LAUNCH_CHECK("dw_fwd");
     if (part_rows) *part_rows = d.B * grid.x;
     return 0;
@@ -416,41 +436,44 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
 // =================================================================================
 // M5  BN2 + ELU + AvgPool2d((1,P1)) + dropout -> d1[n,g,u]
 // =================================================================================
-__global__ void pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
-                                 const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1,
-                                 int dropout_mode, float p_drop, uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_ptr,
-                                 int64_t total, float *__restrict__ d1) {
+// One warp per (n, g) row: no per-element index divisions, lanes walk the pooled positions.
+__global__ void __launch_bounds__(256)
+pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
+                 const uint8_t *__restrict__ mask1, int B, int G, int T, int T4, int P1,
+                 int dropout_mode, float p_drop, uint64_t seed, uint64_t step, const unsigned long long *__restrict__ step_ptr,
+                 int64_t rows, float *__restrict__ d1) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
     if (step_ptr) step = *step_ptr;
     const float inv_keep = (dropout_mode != EAV_DROPOUT_NONE && p_drop < 1.f) ? 1.f / (1.f - p_drop) : 1.f;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int u = (int)(i % T4);
-        int64_t ng = i / T4;
-        int g = (int)(ng % G);
-        int n = (int)(ng / G);
-        const float4 st = bn2[(int64_t)(n / B) * G + g];
-        const float *src = y2 + ng * (int64_t)T + (int64_t)u * P1;
+    const int g = (int)(row % G), n = (int)(row / G);
+    const float4 st = bn2[(int64_t)(n / B) * G + g];
+    const float *src = y2 + row * (int64_t)T;
+    const bool vec = P1 == 4 && (T & 3) == 0;      // one aligned 128-bit load per pooling window
+    const float invp = 1.f / (float)P1;
+    for (int u = lane; u < T4; u += 32) {
         float s = 0.f;
-        if (P1 == 4 && (T & 3) == 0) {       // one aligned 128-bit load per pooling window
-            const float4 v = *reinterpret_cast<const float4 *>(src);
+        if (vec) {
+            const float4 v = *reinterpret_cast<const float4 *>(src + 4 * u);
             s = elu_f(fmaf(v.x, st.z, st.w)) + elu_f(fmaf(v.y, st.z, st.w)) + elu_f(fmaf(v.z, st.z, st.w)) +
                 elu_f(fmaf(v.w, st.z, st.w));
         } else {
-            for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+            for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[u * P1 + w], st.z, st.w));
         }
-        s *= 1.f / (float)P1;
-        if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[i] ? s * inv_keep : 0.f;
-        else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 1u, (uint64_t)i, p_drop) ? s * inv_keep : 0.f;
-        d1[i] = s;
+        s *= invp;
+        const int64_t e = row * T4 + u;
+        if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[e] ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 1u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        d1[e] = s;
     }
 }
 
 int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const uint8_t *mask1,
                      float *d1, cudaStream_t st) {
-    int64_t total = (int64_t)d.N * d.G * d.T4;
-    int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
-    pool1_fwd_kernel<<<blocks, 256, 0, st>>>(y2, bn2, mask1, d.B, d.G, d.T, d.T4, d.P1, d.dropout_mode,
-                                             d.p_drop, d.seed, d.step, d.step_ptr, total, d1);
+    const int64_t rows = (int64_t)d.N * d.G;
+    pool1_fwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(y2, bn2, mask1, d.B, d.G, d.T, d.T4, d.P1, d.dropout_mode,
+                                                               d.p_drop, d.seed, d.step, d.step_ptr, rows, d1);
     EAV_CUDA_LAUNCH_CHECK("pool1_fwd");
     return 0;
 }
