@@ -156,7 +156,7 @@ def run_reference(args):
                              "sample": f"{budget_steps} B=32 train steps (fwd+bwd+Adam, {args.bn_mode}-mode BN) of one subject model; "
                                        "oracle/eegnet_oracle.py restatement of CNN_torch/EEGNet_tor.py on torch-CPU"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -181,8 +181,26 @@ def synth_raw_device(S, seed, device):
     return raw, labels
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr, so that
+    the single JSON line is the only thing this process ever writes to stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -471,7 +489,7 @@ def main():
         line["cpu_baseline"] = cpu
     if pre is not None:
         line["preprocess"] = pre
-    print(json.dumps(line))
+    _emit(line)
 
 
 if __name__ == "__main__":
