@@ -419,7 +419,8 @@ def main():
         tot = sum(stages.values())
         dom = max(("tconv_fwd", "tconv_bwd_dw"), key=lambda k: stages[k])
         peak = ops.measure_fp32_peak()
-        peak_outer = ops.measure_fp32_peak(outer_product=True)
+        peak_outer = ops.measure_fp32_peak(1)
+        peak_ffma2 = ops.measure_fp32_peak(3)
         ach = TCONV_FLOP_PER_SAMPLE * M * B / (stages[dom] * 1e-3) / 1e12
         traffic = None
         try:
@@ -432,11 +433,12 @@ def main():
                                "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s. MEASURED_PEAKS.json holds "
                                "only HBM and bf16-tensor peaks; this kernel runs on the fp32 CUDA cores by design "
                                "(1e-4 parity budget rules out TF32, north_star)",
-                "peak_register_operands": peak_outer,
-                "frac_of_register_operand_peak": ach / peak_outer,
-                "peak_register_operands_note": "same device, 8x8 register outer product (three register operands per "
-                                               "FFMA, the instruction mix of a register-blocked convolution): the "
-                                               "register file, not the FMA pipe, caps this form",
+                "ceilings": {"register_outer_product_ffma": peak_outer, "register_outer_product_ffma2": peak_ffma2,
+                             "frac_of_ffma2_ceiling": ach / peak_ffma2,
+                             "note": "same device, 8x8 register outer product (the instruction mix of a register-blocked "
+                                     "convolution): scalar FFMA with three register operands, and Blackwell packed FFMA2 "
+                                     "(fma.rn.f32x2), which both conv kernels use.  The register file, not the FMA pipe, "
+                                     "caps these forms; `peak` is the pipe peak (immediate-operand FFMA)"},
                 "algorithmic_flops_per_launch": TCONV_FLOP_PER_SAMPLE * M * B,
                 "whole_step": {"achieved": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                                "frac": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12 / peak}}

@@ -63,6 +63,7 @@ SYMBOLS = {
     "eav_renorm_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),
+    "eav_measure_fp32_peak_mode": (c_int, [c_int, POINTER(c_double), c_void_p]),
 }
 
 _lib = None

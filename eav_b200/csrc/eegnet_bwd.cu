@@ -743,8 +743,8 @@ int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const flo
 constexpr int TW_WARPS = 4;
 constexpr int TW_TCH = 128;     // time steps of dy1 staged per pass
 
-template <int F1, int RK>
-__global__ void __launch_bounds__(TW_WARPS * 32, 3)
+template <int F1, int RK, int MINB>
+__global__ void __launch_bounds__(TW_WARPS * 32, MINB)
 tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
                     const float *__restrict__ dz1, const float *__restrict__ y1,
                     const float4 *__restrict__ bnf1, const float4 *__restrict__ bnb1, int bn_train, int B,
@@ -753,17 +753,20 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
     const int Tp = (T + 3) & ~3;
     const int XS = (Tp + 32 * RK + 8 + 3) & ~3;      // x row incl. both paddings
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *xs = smem + warp * (XS + TW_TCH * F1);    // per-warp private staging
-    float *dys = xs + XS;                            // [F1][TW_TCH]
+    constexpr int DYS = TW_TCH * F1 + (TW_TCH / 4) * 4;   // [t][F1] rows, +4 floats after every 4 rows (bank spread)
+    float *xs = smem + warp * (XS + DYS);            // per-warp private staging
+    float *dys = xs + XS;                            // dys[t*F1 + (t/4)*4 + f]
     const int m = blockIdx.x / ctas_per_model, j = blockIdx.x - m * ctas_per_model;
     const int rows = B * C;                          // rows of this model
     const int r_lo = (int)((int64_t)rows * j / ctas_per_model), r_hi = (int)((int64_t)rows * (j + 1) / ctas_per_model);
 
-    float acc[F1][RK];
+    // Packed fp32 (FFMA2): float2 accumulators over filter PAIRS; dy1 pairs come out of the [t][f]
+    // LDS.128, the x operand is the scalar-broadcast form.
+    float2 acc2[F1 / 2][RK];
 #pragma unroll
-    for (int f = 0; f < F1; ++f)
+    for (int p = 0; p < F1 / 2; ++p)
 #pragma unroll
-        for (int q = 0; q < RK; ++q) acc[f][q] = 0.f;
+        for (int q = 0; q < RK; ++q) acc2[p][q] = make_float2(0.f, 0.f);
 
     const bool vec_ok = (T & 3) == 0;
     for (int r = r_lo + warp; r < r_hi; r += TW_WARPS) {
@@ -796,28 +799,33 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
                 const int t = 4 * lane;
                 const bool act = t < tn;              // T % 4 == 0: the whole float4 is in range
 #pragma unroll
-                for (int fh = 0; fh < F1; fh += 4) {
-                    float4 dzv[4], yv[4];
+                for (int fh = 0; fh < F1; fh += 2) {       // two filters at a time keeps the staging registers low
+                    float4 dzv[2], yv[2], o[2];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int64_t base = ((n * F1 + fh + q) * C + c) * (int64_t)T + tc + t;
                         dzv[q] = act ? *reinterpret_cast<const float4 *>(dz1 + base) : make_float4(0.f, 0.f, 0.f, 0.f);
                         if (bn_train) yv[q] = act ? *reinterpret_cast<const float4 *>(y1 + base) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const float4 kb = bnb1[(int64_t)m * F1 + fh + q];
-                        float4 o;
                         if (bn_train) {
                             const float4 kf = bnf1[(int64_t)m * F1 + fh + q];
-                            o.x = kb.x * (dzv[q].x - kb.y - (yv[q].x - kf.x) * kf.y * kb.z);
-                            o.y = kb.x * (dzv[q].y - kb.y - (yv[q].y - kf.x) * kf.y * kb.z);
-                            o.z = kb.x * (dzv[q].z - kb.y - (yv[q].z - kf.x) * kf.y * kb.z);
-                            o.w = kb.x * (dzv[q].w - kb.y - (yv[q].w - kf.x) * kf.y * kb.z);
+                            o[q].x = kb.x * (dzv[q].x - kb.y - (yv[q].x - kf.x) * kf.y * kb.z);
+                            o[q].y = kb.x * (dzv[q].y - kb.y - (yv[q].y - kf.x) * kf.y * kb.z);
+                            o[q].z = kb.x * (dzv[q].z - kb.y - (yv[q].z - kf.x) * kf.y * kb.z);
+                            o[q].w = kb.x * (dzv[q].w - kb.y - (yv[q].w - kf.x) * kf.y * kb.z);
                         } else {
-                            o = make_float4(kb.x * dzv[q].x, kb.x * dzv[q].y, kb.x * dzv[q].z, kb.x * dzv[q].w);
+                            o[q] = make_float4(kb.x * dzv[q].x, kb.x * dzv[q].y, kb.x * dzv[q].z, kb.x * dzv[q].w);
                         }
-                        if (act) *reinterpret_cast<float4 *>(dys + (fh + q) * TW_TCH + t) = o;
+                    }
+                    if (act) {      // register transpose: one float2 over 2 filters per time step
+                        float *d = dys + t * F1 + t + fh;          // t*F1 + (t/4)*4 with t % 4 == 0
+                        *reinterpret_cast<float2 *>(d) = make_float2(o[0].x, o[1].x);
+                        *reinterpret_cast<float2 *>(d + F1) = make_float2(o[0].y, o[1].y);
+                        *reinterpret_cast<float2 *>(d + 2 * F1) = make_float2(o[0].z, o[1].z);
+                        *reinterpret_cast<float2 *>(d + 3 * F1) = make_float2(o[0].w, o[1].w);
                     }
                 }
             } else {
@@ -833,7 +841,7 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
                             if (bn_train) v = kb.x * (v - kb.y - (y1[base + t] - kf.x) * kf.y * kb.z);
                             else v = kb.x * v;
                         }
-                        dys[f * TW_TCH + t] = v;
+                        dys[t * F1 + (t >> 2) * 4 + f] = v;
                     }
                 }
             }
@@ -847,18 +855,23 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
                     float2 v = *reinterpret_cast<const float2 *>(xr + t + 2 * q);
                     xw[2 * q] = v.x; xw[2 * q + 1] = v.y;
                 }
-                float dv[F1][4];
+                const float *dr = dys + t * F1 + t;        // rows t..t+3 are contiguous (pad comes after them)
 #pragma unroll
-                for (int f = 0; f < F1; ++f) {
-                    float4 v = *reinterpret_cast<const float4 *>(dys + f * TW_TCH + t);
-                    dv[f][0] = v.x; dv[f][1] = v.y; dv[f][2] = v.z; dv[f][3] = v.w;
+                for (int tt = 0; tt < 4; ++tt) {
+                    float2 dv2[F1 / 2];
+#pragma unroll
+                    for (int h = 0; h < F1 / 4; ++h) {
+                        const float4 v = *reinterpret_cast<const float4 *>(dr + tt * F1 + 4 * h);
+                        dv2[2 * h] = make_float2(v.x, v.y);
+                        dv2[2 * h + 1] = make_float2(v.z, v.w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < RK; ++q) {
+                        const float2 xx = make_float2(xw[tt + q], xw[tt + q]);
+#pragma unroll
+                        for (int p = 0; p < F1 / 2; ++p) acc2[p][q] = __ffma2_rn(dv2[p], xx, acc2[p][q]);
+                    }
                 }
-#pragma unroll
-                for (int tt = 0; tt < 4; ++tt)
-#pragma unroll
-                    for (int f = 0; f < F1; ++f)
-#pragma unroll
-                        for (int q = 0; q < RK; ++q) acc[f][q] = fmaf(dv[f][tt], xw[tt + q], acc[f][q]);
             }
         }
     }
@@ -866,9 +879,12 @@ tconv_bwd_dw_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
     __syncthreads();
     float *red = smem;   // [TW_WARPS][F1][32*RK]
 #pragma unroll
-    for (int f = 0; f < F1; ++f)
+    for (int p = 0; p < F1 / 2; ++p)
 #pragma unroll
-        for (int q = 0; q < RK; ++q) red[(warp * F1 + f) * (32 * RK) + lane * RK + q] = acc[f][q];
+        for (int q = 0; q < RK; ++q) {
+            red[(warp * F1 + 2 * p) * (32 * RK) + lane * RK + q] = acc2[p][q].x;
+            red[(warp * F1 + 2 * p + 1) * (32 * RK) + lane * RK + q] = acc2[p][q].y;
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < F1 * K1; i += blockDim.x) {
         int f = i / K1, k = i - f * K1;
@@ -883,7 +899,7 @@ template <int RK>
 static size_t tconv_dw_smem(int T) {
     const int Tp = (T + 3) & ~3;
     const int XS = (Tp + 32 * RK + 8 + 3) & ~3;
-    size_t stage = (size_t)TW_WARPS * (XS + TW_TCH * 8) * sizeof(float);
+    size_t stage = (size_t)TW_WARPS * (XS + TW_TCH * 8 + (TW_TCH / 4) * 4) * sizeof(float);
     size_t redb = (size_t)TW_WARPS * 8 * 32 * RK * sizeof(float);
     return stage > redb ? stage : redb;
 }
@@ -893,7 +909,9 @@ static int tconv_rk(int K1) { return K1 <= 64 ? 2 : K1 <= 128 ? 4 : K1 <= 256 ? 
 int tconv_dw_ctas_per_model(const NetDims &d) {
     // ~two full waves of resident CTAs (148 SMs x up to 3 CTAs) when the work allows it
     int64_t rows = (int64_t)d.B * d.C;
-    int64_t want = (148 * 3 * 2) / d.M;
+    static int per_sm = -1;
+    if (per_sm < 0) { const char *e = getenv("EAV_TW_MINB"); per_sm = e ? atoi(e) : 3; }
+    int64_t want = (148 * per_sm * 2) / d.M;
     int64_t cap = cdiv64(rows, TW_WARPS);   // at least one row per warp
     int64_t c = want < cap ? want : cap;
     if (c < 1) c = 1;
@@ -908,11 +926,18 @@ static int launch_tconv_bwd_dw_rk(const NetDims &d, const float *x, const int32_
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: Samples=%d too large", d.T);
     static bool attr_set = false;   // one flag per RK instantiation
     if (!attr_set) {
-        cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    tconv_bwd_dw_kernel<8, RK><<<d.M * cpm, TW_WARPS * 32, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train,
-                                                                       d.B, d.C, d.T, d.K1, d.pad1l, cpm, part);
+    static int minb = -1;
+    if (minb < 0) { const char *e = getenv("EAV_TW_MINB"); minb = e ? atoi(e) : 3; }
+    if (minb == 2)
+        tconv_bwd_dw_kernel<8, RK, 2><<<d.M * cpm, TW_WARPS * 32, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train,
+                                                                              d.B, d.C, d.T, d.K1, d.pad1l, cpm, part);
+    else
+        tconv_bwd_dw_kernel<8, RK, 3><<<d.M * cpm, TW_WARPS * 32, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train,
+                                                                              d.B, d.C, d.T, d.K1, d.pad1l, cpm, part);
     return 0;
 }
 

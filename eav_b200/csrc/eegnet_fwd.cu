@@ -14,9 +14,7 @@ namespace eav {
 // the x window, 8 broadcast LDS.128 for the weights and 256 FFMA (95.9 % FFMA issue).
 // Algorithmic work: 2*K1*F1 flop per output sample -> 72.0 MFLOP per EEG epoch.
 // =================================================================================
-constexpr int TC_R = 8;         // outputs per thread
-constexpr int TC_TPR = 64;      // threads per row
-constexpr int TC_TT = TC_R * TC_TPR;  // 512 time outputs per item
+constexpr int TC_TT = 512;      // time outputs per work item (threads per row x outputs per thread)
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -30,13 +28,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // so there is no wave-quantisation tail and the filter bank is re-staged only when the model
 // changes.  The x tile of the NEXT item is fetched with cp.async into the other half of a
 // double buffer while the FFMA loop of the current item runs.
-template <int F1, int TC_ROWS, int KU, int MINB>
-__global__ void __launch_bounds__(TC_ROWS * TC_TPR, MINB)
+template <int F1, int TC_ROWS, int KU, int MINB, int TC_R>
+__global__ void __launch_bounds__(TC_ROWS * (TC_TT / TC_R), MINB)
 tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
                  const float *__restrict__ params, int64_t pstride, int64_t oW1, int B, int C,
                  int T, int K1, int padl, int n_items, int groups, int tiles, float *__restrict__ y1,
                  float *__restrict__ part) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int TC_TPR = TC_TT / TC_R;             // threads per row
     constexpr int TC_THREADS = TC_ROWS * TC_TPR;
     const int K1p = (K1 + KU - 1) / KU * KU;
     const int XS = TC_TT + K1p + 4;  // multiple of 4
@@ -96,11 +95,15 @@ tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_inde
         const int r = tid / TC_TPR, j = tid - r * TC_TPR;
         const int t0 = j * TC_R;
         const float *xr = xs + r * XS + t0;
-        float acc[F1][TC_R];
+        // Packed fp32 (Blackwell FFMA2, fma.rn.f32x2): accumulators are float2 over filter PAIRS, the
+        // weight pairs (w[2p], w[2p+1]) come straight out of the [k][f] LDS.128, the x operand is a
+        // duplicated pair.  Two FMAs per instruction halve the register-file reads per FMA: an 8x8
+        // register outer product measures 63.3 TFLOP/s this way vs 52.7 with scalar FFMA.
+        float2 acc2[F1 / 2][TC_R];
 #pragma unroll
-        for (int f = 0; f < F1; ++f)
+        for (int p = 0; p < F1 / 2; ++p)
 #pragma unroll
-            for (int q = 0; q < TC_R; ++q) acc[f][q] = 0.f;
+            for (int q = 0; q < TC_R; ++q) acc2[p][q] = make_float2(0.f, 0.f);
 
         for (int k0 = 0; k0 < K1p; k0 += KU) {
             float xw[TC_R + KU];
@@ -111,18 +114,26 @@ tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_inde
             }
 #pragma unroll
             for (int kk = 0; kk < KU; ++kk) {
-                float w[F1];
+                float2 w2[F1 / 2];
 #pragma unroll
                 for (int q = 0; q < F1 / 4; ++q) {
                     float4 v = *reinterpret_cast<const float4 *>(ws + (k0 + kk) * F1 + 4 * q);
-                    w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                    w2[2 * q] = make_float2(v.x, v.y);
+                    w2[2 * q + 1] = make_float2(v.z, v.w);
                 }
 #pragma unroll
-                for (int f = 0; f < F1; ++f)
+                for (int q = 0; q < TC_R; ++q) {
+                    const float2 xx = make_float2(xw[kk + q], xw[kk + q]);
 #pragma unroll
-                    for (int q = 0; q < TC_R; ++q) acc[f][q] = fmaf(w[f], xw[kk + q], acc[f][q]);
+                    for (int p = 0; p < F1 / 2; ++p) acc2[p][q] = __ffma2_rn(w2[p], xx, acc2[p][q]);
+                }
             }
         }
+        float acc[F1][TC_R];
+#pragma unroll
+        for (int p = 0; p < F1 / 2; ++p)
+#pragma unroll
+            for (int q = 0; q < TC_R; ++q) { acc[2 * p][q] = acc2[p][q].x; acc[2 * p + 1][q] = acc2[p][q].y; }
 
         const int c = c0 + r;
         const int tg = tile0 + t0;
@@ -132,8 +143,9 @@ tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_inde
             for (int f = 0; f < F1; ++f) {
                 float *dst = y1 + (((int64_t)n * F1 + f) * C + c) * (int64_t)T + tg;
                 if ((T & 3) == 0 && tg + TC_R <= T) {
-                    reinterpret_cast<float4 *>(dst)[0] = make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
-                    reinterpret_cast<float4 *>(dst)[1] = make_float4(acc[f][4], acc[f][5], acc[f][6], acc[f][7]);
+#pragma unroll
+                    for (int q4 = 0; q4 < TC_R / 4; ++q4)
+                        reinterpret_cast<float4 *>(dst)[q4] = make_float4(acc[f][4 * q4], acc[f][4 * q4 + 1], acc[f][4 * q4 + 2], acc[f][4 * q4 + 3]);
                 } else {
 #pragma unroll
                     for (int q = 0; q < TC_R; ++q)
@@ -171,18 +183,17 @@ tconv_fwd_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_inde
 // variant table (EAV_TC_VARIANT env var for A/B runs; default = the fastest measured)
 static int tc_variant() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("EAV_TC_VARIANT"); v = e ? atoi(e) : 2; }   // measured on B200: 2 (4 rows, 4 taps/iter) 1.91 ms, 0: 2.02, 1: 2.08, 3: 1.93
+    if (v < 0) { const char *e = getenv("EAV_TC_VARIANT"); v = e ? atoi(e) : 3; }   // measured on B200 with FFMA2: 3 (4 rows, 8 taps/iter) 1.76 ms, 2: 1.83, 6: 1.84, 5: 1.85, 4: 1.90
     return v;
 }
-static int tc_rows() { int v = tc_variant(); return (v == 2 || v == 3) ? 4 : 3; }
-static int tc_ku() { int v = tc_variant(); return (v == 1 || v == 3) ? 8 : 4; }
+static int tc_rows() { int v = tc_variant(); return (v == 0 || v == 1) ? 3 : (v == 5 ? 8 : 4); }
 
 int tconv_fwd_rows_per_sample(const NetDims &d) { return cdiv(d.C, tc_rows()) * cdiv(d.T, TC_TT); }
 
-template <int ROWS, int KU, int MINB>
+template <int ROWS, int KU, int MINB, int R>
 static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
                               float *y1, float *part, int *part_rows, cudaStream_t st) {
-    constexpr int THREADS = ROWS * TC_TPR;
+    constexpr int THREADS = ROWS * (TC_TT / R);
     const int K1p = (d.K1 + KU - 1) / KU * KU;
     const int XS = TC_TT + K1p + 4;
     size_t smem = (size_t)(K1p * d.F1 + 2 * ROWS * XS) * sizeof(float);
@@ -192,17 +203,17 @@ static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x
     static int resident = 0;          // CTAs the device holds at once (SMs x occupancy)
     static size_t resident_smem = 0;
     if (resident == 0 || resident_smem != smem) {
-        cudaFuncSetAttribute(tconv_fwd_kernel<8, ROWS, KU, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tconv_fwd_kernel<8, ROWS, KU, MINB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int dev = 0, sms = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tconv_fwd_kernel<8, ROWS, KU, MINB>, THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tconv_fwd_kernel<8, ROWS, KU, MINB, R>, THREADS, smem);
         resident = sms * (per_sm > 0 ? per_sm : 1);
         resident_smem = smem;
     }
     const int grid = (int)(n_items < resident ? n_items : resident);
-    tconv_fwd_kernel<8, ROWS, KU, MINB><<<grid, THREADS, smem, st>>>(x, x_index, params, d.pstride, d.oW1, d.B, d.C, d.T,
-                                                                    d.K1, d.pad1l, (int)n_items, groups, tiles, y1, part);
+    tconv_fwd_kernel<8, ROWS, KU, MINB, R><<<grid, THREADS, smem, st>>>(x, x_index, params, d.pstride, d.oW1, d.B, d.C, d.T,
+                                                                       d.K1, d.pad1l, (int)n_items, groups, tiles, y1, part);
     EAV_CUDA_LAUNCH_CHECK("tconv_fwd");
     if (part_rows) *part_rows = d.B * groups * tiles;
     return 0;
@@ -212,10 +223,13 @@ int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, c
                      float *y1, float *part, int *part_rows, cudaStream_t st) {
     EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_fwd: F1=%d unsupported (only 8)", d.F1);
     switch (tc_variant()) {
-        case 1: return launch_tconv_fwd_v<3, 8, 3>(d, x, x_index, params, y1, part, part_rows, st);
-        case 2: return launch_tconv_fwd_v<4, 4, 2>(d, x, x_index, params, y1, part, part_rows, st);
-        case 3: return launch_tconv_fwd_v<4, 8, 2>(d, x, x_index, params, y1, part, part_rows, st);
-        default: return launch_tconv_fwd_v<3, 4, 3>(d, x, x_index, params, y1, part, part_rows, st);
+        case 0: return launch_tconv_fwd_v<3, 4, 3, 8>(d, x, x_index, params, y1, part, part_rows, st);
+        case 1: return launch_tconv_fwd_v<3, 8, 3, 8>(d, x, x_index, params, y1, part, part_rows, st);
+        case 3: return launch_tconv_fwd_v<4, 8, 2, 8>(d, x, x_index, params, y1, part, part_rows, st);
+        case 4: return launch_tconv_fwd_v<4, 4, 3, 16>(d, x, x_index, params, y1, part, part_rows, st);   // 128 thr, 16 outputs/thread
+        case 5: return launch_tconv_fwd_v<8, 4, 1, 16>(d, x, x_index, params, y1, part, part_rows, st);   // 256 thr, 16 outputs/thread
+        case 6: return launch_tconv_fwd_v<4, 8, 3, 16>(d, x, x_index, params, y1, part, part_rows, st);
+        default: return launch_tconv_fwd_v<4, 4, 2, 8>(d, x, x_index, params, y1, part, part_rows, st);
     }
 }
 

@@ -169,6 +169,35 @@ ffma_outer_kernel(float *out, const float *in, int iters) {
     if (s == 123.456f) out[0] = s;
 }
 
+// Blackwell packed fp32: FFMA2 (fma.rn.f32x2) does two FMAs per lane on 64-bit register pairs,
+// i.e. half the operand fetches per FMA.  Same 8x8 outer product, accumulators held as float2.
+__global__ void __launch_bounds__(256)
+ffma2_outer_kernel(float *out, const float *in, int iters) {
+    float2 a[8], b[4], acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { float v = in[threadIdx.x + 32 * i]; a[i] = make_float2(v, v); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = make_float2(in[threadIdx.x + 64 * j + 256], in[threadIdx.x + 64 * j + 288]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rot = 0; rot < 8; ++rot)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(a[(i + rot) & 7], b[j], acc[i][j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j].x + acc[i][j].y;
+    if (s == 123.456f) out[0] = s;
+}
+
 // Third form: one operand of every FFMA comes from the constant bank through a uniform
 // register (LDCU -> UR), as the FIR taps do: acc[i][j] += a[i] * c_tab[k][j].
 __constant__ float c_peak_tab[256 * 8];
@@ -255,44 +284,51 @@ extern "C" int eav_eegnet_loss(const eav_eegnet_cfg *cfg, const float *out, cons
     return 0;
 }
 
-extern "C" int eav_measure_fp32_peak_outer(double *tflops, void *stream) {
-    EAV_REQUIRE(tflops, EAV_ERR_BAD_ARG, "measure_fp32_peak_outer: null pointer");
+// mode 1: scalar FFMA, three register operands; 2: one operand from a uniform register (constant bank);
+// 3: packed FFMA2.  All are the same 8x8 register outer product.
+extern "C" int eav_measure_fp32_peak_mode(int mode, double *tflops, void *stream) {
+    EAV_REQUIRE(tflops, EAV_ERR_BAD_ARG, "measure_fp32_peak_mode: null pointer");
+    if (mode == 0) return eav_measure_fp32_peak(tflops, stream);
+    EAV_REQUIRE(mode >= 1 && mode <= 3, EAV_ERR_BAD_ARG, "measure_fp32_peak_mode: mode %d", mode);
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     float *buf = nullptr;
-    if (cudaMalloc(&buf, 4096 * sizeof(float)) != cudaSuccess) { set_error("measure_fp32_peak_outer: cudaMalloc failed"); return (int)cudaErrorMemoryAllocation; }
+    if (cudaMalloc(&buf, 4096 * sizeof(float)) != cudaSuccess) { set_error("measure_fp32_peak_mode: cudaMalloc failed"); return (int)cudaErrorMemoryAllocation; }
     cudaMemsetAsync(buf, 0, 4096 * sizeof(float), st);
     const int iters = 1024, blocks = sms * 8;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const bool use_const = getenv("EAV_PEAK_CONST") != nullptr;    // experiment: uniform-register operand form
-    if (use_const) ffma_outer_const_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 1);
-    else ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, 16);
+    auto launch = [&](int n) {
+        if (mode == 1) ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, n);
+        else if (mode == 2) ffma_outer_const_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, n / 32 > 0 ? n / 32 : 1);
+        else ffma2_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, n);
+    };
+    launch(32);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(e0, st);
-        if (use_const) ffma_outer_const_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters / 32);
-        else ffma_outer_kernel<<<blocks, 256, 0, st>>>(buf, buf + 1024, iters);
+        launch(iters);
         cudaEventRecord(e1, st);
         cudaEventSynchronize(e1);
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        double per_iter = use_const ? 256.0 * 64 : 512.0;
-        double n_it = use_const ? iters / 32 : iters;
-        double tf = 2.0 * per_iter * n_it * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        const double fma_per_thread = (mode == 2) ? 256.0 * 64 * (iters / 32) : 512.0 * iters;
+        const double tf = 2.0 * fma_per_thread * 256.0 * blocks / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(buf);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error("measure_fp32_peak_outer: %s", cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { set_error("measure_fp32_peak_mode: %s", cudaGetErrorString(e)); return (int)e; }
     *tflops = best;
     return 0;
 }
+
+extern "C" int eav_measure_fp32_peak_outer(double *tflops, void *stream) { return eav_measure_fp32_peak_mode(1, tflops, stream); }
 
 extern "C" int eav_measure_fp32_peak(double *tflops, void *stream) {
     EAV_REQUIRE(tflops, EAV_ERR_BAD_ARG, "measure_fp32_peak: null pointer");

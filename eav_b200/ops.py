@@ -212,12 +212,13 @@ def renorm_rows(w2d, maxnorm):
                "eav_renorm_rows")
 
 
-def measure_fp32_peak(outer_product=False) -> float:
-    """Measured fp32 TFLOP/s: register-resident FFMA loop (default) or an 8x8 register outer product."""
+def measure_fp32_peak(mode=0) -> float:
+    """Measured fp32 TFLOP/s of this device.  mode 0: register-resident FFMA loop with immediate /
+    uniform operands (the pipe peak); 1: 8x8 register outer product with scalar FFMA; 2: the same with
+    one operand in a uniform register; 3: the same with packed FFMA2 (fma.rn.f32x2)."""
     _lib.require_device()
     v = ctypes.c_double(0.0)
-    fn = _lib.load().eav_measure_fp32_peak_outer if outer_product else _lib.load().eav_measure_fp32_peak
-    _lib.check(fn(ctypes.byref(v), _stream()), "eav_measure_fp32_peak")
+    _lib.check(_lib.load().eav_measure_fp32_peak_mode(int(mode), ctypes.byref(v), _stream()), "eav_measure_fp32_peak_mode")
     return v.value
 
 

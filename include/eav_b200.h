@@ -239,6 +239,9 @@ int eav_measure_fp32_peak(double *tflops, void *stream);
 /* Same, for an 8x8 register outer product (three register operands per FFMA): the practical
  * ceiling of a register-blocked fp32 convolution/GEMM kernel on the CUDA cores. */
 int eav_measure_fp32_peak_outer(double *tflops, void *stream);
+/* mode 0: immediate form; 1: register outer product, scalar FFMA; 2: same with one operand in a uniform
+ * register (constant bank); 3: same with Blackwell packed FFMA2 (fma.rn.f32x2). */
+int eav_measure_fp32_peak_mode(int mode, double *tflops, void *stream);
 
 #ifdef __cplusplus
 }

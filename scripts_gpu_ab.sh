@@ -1,3 +1,4 @@
 #!/bin/bash
-python scripts/kbench.py --stages dw_fwd,dw_bwd,pool1_fwd,pool1_bwd,tail_fwd,tail_bwd --reps 20
-python -m pytest tests/test_gpu_eegnet.py -m gpu -q 2>&1 | tail -2
+for b in 3 2; do echo "minb $b"; EAV_TW_MINB=$b python scripts/kbench.py --stages tconv_bwd_dw --reps 20; done
+python -m pytest tests/test_gpu_eegnet.py -m gpu -q 2>&1 | tail -1
+EAV_TW_MINB=2 python -m pytest tests/test_gpu_eegnet.py -m gpu -q 2>&1 | tail -1
