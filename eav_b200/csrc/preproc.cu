@@ -463,6 +463,22 @@ __global__ void invert_slots_kernel(const int32_t *__restrict__ epoch_slot, int 
     if (slot >= 0 && slot < n_kept) kept_trial[(int64_t)subj * n_kept + slot] = trial;
 }
 
+// helper stream for overlapping the fp64 SOS passes with the next group's FIR (one per device)
+struct PreSide { cudaStream_t stream; cudaEvent_t fork[4], join; };
+static PreSide *pre_side_stream() {
+    static PreSide pool[64];
+    static bool made[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!made[dev]) {
+        if (cudaStreamCreateWithFlags(&pool[dev].stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&pool[dev].fork[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&pool[dev].join, cudaEventDisableTiming);
+        made[dev] = true;
+    }
+    return &pool[dev];
+}
+
 struct PreLayout { size_t dec, z, start, kept, gtab, total; };
 static PreLayout pre_layout(const eav_preproc_cfg *c, bool own_dec) {
     PreLayout l;
@@ -696,16 +712,55 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
         for (int t = 0; t < cfg->n_taps; ++t)
             if (t != Hh && ((t - Hh) % cfg->down) == 0 && fabs(taps[t]) > 1e-15 * fabs(taps[Hh])) skip_zero = false;
     }
-    if (cfg->raw_is_f64) rc = run_fir<double>(cfg, reinterpret_cast<const double *>(raw), ft, skip_zero, dec, st);
-    else rc = run_fir<float>(cfg, reinterpret_cast<const float *>(raw), ft, skip_zero, dec, st);
-    if (rc) return rc;
-
-    switch (NSEC) {
-        case 1: return run_sos<1>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
-        case 2: return run_sos<2>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
-        case 3: return run_sos<3>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
-        case 4: return run_sos<4>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
-        case 5: return run_sos<5>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
-        default: return run_sos<6>(cfg, dec, co, A, gtab, kept, n_kept, z, start, n_epochs_out, epochs, st);
+    // Optional grouping (EAV_PREPROC_GROUPS=n): the FIR of group i+1 on the caller's stream, the SOS
+    // passes of group i on a forked stream.  The idea was to overlap the fp32/HBM-bound FIR with the
+    // fp64-bound SOS passes; measured on B200 it does NOT pay (42 subjects: 1 group 4.42 ms, 2: 4.78,
+    // 3: 5.15, 6: 6.76 -- the FIR grid saturates every SM's CTA slots, so the forked kernels only
+    // run in its tail), hence one group by default.
+    const int S = cfg->n_subjects;
+    int n_groups = 1;
+    {
+        static int forced = -1;
+        if (forced < 0) { const char *e = getenv("EAV_PREPROC_GROUPS"); forced = e ? atoi(e) : 0; }
+        if (forced > 0) n_groups = forced < S ? forced : S;
     }
+    PreSide *side = n_groups > 1 ? pre_side_stream() : nullptr;
+    if (side == nullptr) n_groups = 1;
+    const size_t raw_subj = (size_t)cfg->n_trials * cfg->n_chans * cfg->trial_len;          // elements
+    const size_t dec_subj = (size_t)cfg->n_chans * cfg->n_trials * chunk;
+    const size_t st_subj = (size_t)cfg->n_chans * cfg->n_trials * NS;
+    const size_t ep_subj = (size_t)n_epochs_out * cfg->n_chans * (chunk / cfg->n_sub);
+    for (int g = 0; g < n_groups; ++g) {
+        const int s0 = (int)((int64_t)S * g / n_groups), s1 = (int)((int64_t)S * (g + 1) / n_groups);
+        if (s1 <= s0) continue;
+        eav_preproc_cfg sub = *cfg;
+        sub.n_subjects = s1 - s0;
+        float *dec_g = dec + s0 * dec_subj;
+        if (cfg->raw_is_f64) rc = run_fir<double>(&sub, reinterpret_cast<const double *>(raw) + s0 * raw_subj, ft, skip_zero, dec_g, st);
+        else rc = run_fir<float>(&sub, reinterpret_cast<const float *>(raw) + s0 * raw_subj, ft, skip_zero, dec_g, st);
+        if (rc) return rc;
+        cudaStream_t sst = st;
+        if (side != nullptr) {
+            cudaEventRecord(side->fork[g % 4], st);
+            cudaStreamWaitEvent(side->stream, side->fork[g % 4], 0);
+            sst = side->stream;
+        }
+        double *z_g = z + s0 * st_subj, *start_g = start + s0 * st_subj;
+        const int32_t *kept_g = kept + (size_t)s0 * n_kept;
+        float *ep_g = epochs ? epochs + s0 * ep_subj : nullptr;
+        switch (NSEC) {
+            case 1: rc = run_sos<1>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+            case 2: rc = run_sos<2>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+            case 3: rc = run_sos<3>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+            case 4: rc = run_sos<4>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+            case 5: rc = run_sos<5>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+            default: rc = run_sos<6>(&sub, dec_g, co, A, gtab, kept_g, n_kept, z_g, start_g, n_epochs_out, ep_g, sst); break;
+        }
+        if (rc) return rc;
+    }
+    if (side != nullptr) {
+        cudaEventRecord(side->join, side->stream);
+        cudaStreamWaitEvent(st, side->join, 0);
+    }
+    return 0;
 }

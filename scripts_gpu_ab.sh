@@ -1,4 +1,4 @@
 #!/bin/bash
-for b in 3 2; do echo "minb $b"; EAV_TW_MINB=$b python scripts/kbench.py --stages tconv_bwd_dw --reps 20; done
-python -m pytest tests/test_gpu_eegnet.py -m gpu -q 2>&1 | tail -1
-EAV_TW_MINB=2 python -m pytest tests/test_gpu_eegnet.py -m gpu -q 2>&1 | tail -1
+python -m pytest tests/test_gpu_preproc.py tests/test_gpu_dropin.py::test_dataload_eeg_dropin_vs_oracle -m gpu -q 2>&1 | tail -1
+for g in 1 2 3 6; do echo "groups $g"; EAV_PREPROC_GROUPS=$g python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-stages 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['preprocess']['ms'], d['preprocess']['value'], d['preprocess']['roofline']['frac'])"; done
