@@ -136,3 +136,54 @@ def test_cnn_eeg_trainer_runs_and_learns():
     assert last < first and np.isfinite(vloss) and 0 <= acc <= 100
     preds = tr.predict()
     assert len(preds) == 16 and all(isinstance(p, int) for p in preds)
+
+
+def test_dataload_eeg_mat_file_path_end_to_end(tmp_path):
+    """P1: the .mat layout the reference reads (Datasets/EAV/subjectNN/EEG/subjectNN_eeg.mat with 'seg',
+    subjectNN_eeg_label.mat with 'label'; Dataload_eeg.py:54-83) through prepare_data() and its legacy alias."""
+    import scipy.io
+    import eeg_oracle as O
+    from eav_b200.Dataload_eeg import DataLoadEEG
+    raw, label = O.synth_subject(5)
+    folder = tmp_path / "subject05" / "EEG"
+    folder.mkdir(parents=True)
+    scipy.io.savemat(str(folder / "subject05_eeg.mat"), {"seg": np.transpose(raw, (2, 1, 0))})      # (10000, 30, 200)
+    scipy.io.savemat(str(folder / "subject05_eeg_label.mat"), {"label": label})
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        d = DataLoadEEG(subject=5, band=[0.5, 45], fs_orig=500, fs_target=100, parent_directory=str(tmp_path))
+        x, y = d.data_prepare()
+    assert "[Info] Loaded EEG data for subject05" in out.getvalue()
+    xo, yo = O.prepare_data(raw, label, [0.5, 45])
+    assert x.shape == (400, 30, 500) and x.dtype == np.float32 and np.array_equal(y, yo)
+    rms = np.sqrt((xo ** 2).mean(axis=(0, 2)))
+    assert (np.abs(x - xo).max(axis=(0, 2)) / rms).max() < 1e-5
+    assert d.seg_f_div_device.is_cuda and d.seg.shape == (30, 10000, 200)
+    # a missing subject prints the reference's error line and returns the empty placeholders
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        assert DataLoadEEG(subject=6, parent_directory=str(tmp_path)).prepare_data() == (None, None)
+    assert "[Error] EEG data not found for subject06" in out.getvalue()
+
+
+def test_trainer_uni_validate_matches_oracle(golden):
+    """Evaluation path: validate() = eval-mode forward over the test loader, mean of the
+    per-batch CE losses and the accuracy, as EEGNet_tor.py:118-135 computes them."""
+    import eegnet_oracle as EO
+    import golden_inputs as GI
+    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor, Trainer_uni
+    g = golden("trainer_uni_3ep.npz")
+    trx, try_, tex, tey = GI.trainer_inputs()
+    model = EEGNet_tor(5)
+    _load_init(model, g)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        trainer = Trainer_uni(model, [trx, try_, tex, tey], lr=1e-3, batch_size=6, num_epochs=1)
+        loss, acc = trainer.validate()
+    params, buffers = EO.split_state(sd, "tor")
+    tot, correct, nb = 0.0, 0, 0
+    with torch.no_grad():
+        for b0 in range(0, 16, 6):                       # batches of 6, 6, 4 (ragged)
+            xb, yb = torch.from_numpy(tex[b0:b0 + 6]), torch.from_numpy(tey[b0:b0 + 6])
+            o = EO.tor_forward(params, buffers, xb, False)
+            tot += float(EO.loss_fn(o, yb)); correct += int((o.argmax(1) == yb).sum()); nb += 1
+    assert abs(loss - tot / nb) < 1e-4 * (tot / nb) and acc == correct / 16
+    assert f"Validation - Loss: {tot / nb:.4f}, Accuracy: {correct / 16:.4f}" in out.getvalue()
