@@ -64,6 +64,7 @@ SYMBOLS = {
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_mode": (c_int, [c_int, POINTER(c_double), c_void_p]),
+    "eav_tc_probe": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

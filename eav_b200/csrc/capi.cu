@@ -111,6 +111,7 @@ WsLayout make_ws_layout(const NetDims &d) {
     w.dy3d = take(d.variant == EAV_VARIANT_CNN ? N * d.G * d.T4 : 0);
     w.dz2 = take(N * d.G * d.T);
     w.dz1 = take(N * d.F1 * d.C * d.T);
+    w.tcw = take(tconv_fwd_tc_scratch_floats(d));
     w.total = o;
     return w;
 }
@@ -238,7 +239,7 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         }
     }
     switch (stage) {
-        case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.y1), pstat, nullptr, st);
+        case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.tcw), WS(float, w.y1), pstat, nullptr, st);
         case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, W * d.B * d.C * d.T, dp_bn ? sums(1, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf1), st);
         case ST_DW_FWD: return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, st);
         case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34)

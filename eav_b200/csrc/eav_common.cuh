@@ -121,6 +121,7 @@ struct WsLayout {
     size_t partw2, partw3;                             // ... depthwise (dW2), block-2 conv (dW3): separate so the
                                                        // dW3 kernels can run on a forked stream
     size_t dz3, dd1, dy3d, dz2, dz1;                   // backward scratch
+    size_t tcw;                                        // packed tensor-core operand of the temporal conv weights
     size_t total;
 };
 WsLayout make_ws_layout(const NetDims &d);

@@ -188,7 +188,10 @@ static int tc_variant() {
 }
 static int tc_rows() { int v = tc_variant(); return (v == 0 || v == 1) ? 3 : (v == 5 ? 8 : 4); }
 
-int tconv_fwd_rows_per_sample(const NetDims &d) { return cdiv(d.C, tc_rows()) * cdiv(d.T, TC_TT); }
+int tconv_fwd_rows_per_sample(const NetDims &d) {
+    if (tconv_fwd_use_tc(d)) return tconv_fwd_tc_rows_per_sample(d);
+    return cdiv(d.C, tc_rows()) * cdiv(d.T, TC_TT);
+}
 
 template <int ROWS, int KU, int MINB, int R>
 static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
@@ -220,7 +223,9 @@ static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x
 }
 
 int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
-                     float *y1, float *part, int *part_rows, cudaStream_t st) {
+                     float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st) {
+    if (tconv_fwd_use_tc(d))   // tcgen05 path (tconv_tc.cu); EAV_TCONV=ffma selects the CUDA-core kernel below
+        return launch_tconv_fwd_tc(d, x, x_index, params, wt_scratch, y1, part, part_rows, st);
     EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_fwd: F1=%d unsupported (only 8)", d.F1);
     switch (tc_variant()) {
         case 0: return launch_tconv_fwd_v<3, 4, 3, 8>(d, x, x_index, params, y1, part, part_rows, st);

@@ -7,8 +7,16 @@ namespace eav {
 
 // ---- forward -------------------------------------------------------------------
 // M1: temporal conv (EEGNet_tor.py:24,51): x -> y1 raw [N][F1][C][T] (+ BN1 partial sums)
+// wt_scratch: tconv_fwd_tc_scratch_floats(d) floats for the packed tensor-core weight operand (may be null
+// when that is 0)
 int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
-                     float *y1, float *part, int *part_rows, cudaStream_t st);
+                     float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st);
+// tensor-core (tcgen05) variant of the temporal convolution, tconv_tc.cu
+bool tconv_fwd_use_tc(const NetDims &d);
+size_t tconv_fwd_tc_scratch_floats(const NetDims &d);
+int tconv_fwd_tc_rows_per_sample(const NetDims &d);
+int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
+                        float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st);
 // M2/M5/M7 statistics: partial sums -> {mean, invstd, scale, shift}; running-stat update
 int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
                        double count, const double *sums, const float *params, float *bn_state, float4 *stats,

@@ -1,0 +1,375 @@
+// Tensor-core (tcgen05 + TMEM) kernels for the temporal convolution of EEGNet block 1
+// (EEGNet_tor.py:24 `nn.Conv2d(1, F1, (1, kernLength), padding='same')` and its weight gradient).
+//
+// Formulation.  One (sample, electrode) row xs[0..] of the zero-padded signal is a plain
+// fp32 array in shared memory.  With  X[col][i] = xs[4*col + i]  the 16-byte chunk (col + i/4) of the raw row IS
+// the 4-element K-slice of matrix row `col`, so the no-swizzle UMMA descriptor {LBO = 16 B, SBO = 128 B}
+// addresses the Toeplitz operand with no im2col copy at all:
+//   forward   D[col][(f,j)] = sum_i X[col][i] * Wt[(f,j)][i],   Wt[(f,j)][i] = w[f][i-j]       (M=128, N=4*F1)
+//   weight gr D'[i][(f,j)]  = sum_col X[col][i] * dY[col][(f,j)], dY[col][(f,j)] = dy[f][4col+j]
+//             dW[f][k]      = sum_j D'[j+k][(f,j)]                                             (M=i, N=4*F1)
+// fp32 accuracy comes from the 3-product tf32 split  hi*hi + hi*lo + lo*hi  accumulated in TMEM (fp32).
+#include <cstdlib>
+#include <cstring>
+
+#include "eav_common.cuh"
+#include "eegnet_kernels.cuh"
+#include "tc_common.cuh"
+#include "../../include/eav_b200.h"
+
+namespace eav {
+
+// ---------------------------------------------------------------------------------------------
+// Probe: runs `reps` x `ksteps` tcgen05.mma.kind::tf32 on a caller-provided shared-memory image with
+// caller-provided descriptors and returns the accumulator tile + the elapsed SM cycles.
+// It exists so that the descriptor address maps in tc_common.cuh are verified on the device
+// (scripts/tc_probe.py) rather than assumed.
+// ---------------------------------------------------------------------------------------------
+struct ProbeArgs {
+    int image_floats, M, N, ksteps, reps, n_acc;
+    int a_off, a_lbo, a_sbo, a_major, a_step;
+    int b_off, b_lbo, b_sbo, b_major, b_step;
+    int a_bits, b_bits;   // OR-ed into bits [32,64) of the A / B shared-memory descriptor (layout_type, base_offset)
+};
+
+__global__ void __launch_bounds__(128) tc_probe_kernel(const float *__restrict__ image, ProbeArgs a,
+                                                       float *__restrict__ d_out, long long *__restrict__ cycles) {
+    extern __shared__ __align__(1024) float sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < a.image_floats; i += 128) sm[i] = image[i];
+    uint32_t ncols = 32;
+    while ((int)ncols < a.N * a.n_acc) ncols <<= 1;
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
+    if (tid == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::mbar_init_fence();
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    long long t0 = 0, t1 = 0;
+    if (warp == 0) {
+        const uint32_t idesc = tc::idesc_tf32(a.M, a.N, a.a_major, a.b_major);
+        const uint32_t base = tc::smem_u32(sm);
+        const uint64_t ad0 = tc::smem_desc(base + a.a_off, a.a_lbo, a.a_sbo) | ((uint64_t)(uint32_t)a.a_bits << 32);
+        const uint64_t bd0 = tc::smem_desc(base + a.b_off, a.b_lbo, a.b_sbo) | ((uint64_t)(uint32_t)a.b_bits << 32);
+        const uint32_t astep = (uint32_t)a.a_step >> 4, bstep = (uint32_t)a.b_step >> 4;
+        const bool leader = tc::elect_one();
+        t0 = clock64();
+        int acc = 0;
+        uint32_t accumulate = 0;
+        for (int r = 0; r < a.reps; ++r) {
+            uint64_t ad = ad0, bd = bd0;
+            for (int ks = 0; ks < a.ksteps; ++ks) {
+                // independent TMEM column ranges break the accumulate dependency chain
+                if (leader) tc::mma_tf32_ss(tmem + acc * a.N, ad, bd, idesc, accumulate);
+                ad += astep;
+                bd += bstep;
+                if (++acc == a.n_acc) { acc = 0; accumulate = 1; }
+            }
+        }
+        if (leader) tc::mma_commit(&bar);
+        __syncwarp();
+    }
+    tc::mbar_wait(&bar, 0);
+    if (tid == 0) {
+        t1 = clock64();
+        cycles[0] = t1 - t0;
+    }
+    tc::tc_fence_after_sync();
+    for (int c0 = 0; c0 < a.N; c0 += 32) {
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d_out[(size_t)tid * a.N + c0 + j] = v[j];
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+}
+
+// =============================================================================================
+// Forward temporal convolution on the tensor cores.
+//
+// Work item = one (sample n, electrode c) row of T samples.  Row buffer xs[PADL + t] = x[t], zeros elsewhere,
+// PADL = padl = (K1-1)/2, so  y[f][4*col + j] = sum_i xs[4*col + i] * w[f][i - j]  with i = j + k in [0, K1+3).
+//   A (M = 128 cols)  = the raw row buffer through the descriptor {K-major, LBO 16 B, SBO 128 B}; k-step ks
+//                       advances the start address by 32 B.  Two copies: hi and lo halves of the tf32 split.
+//   B (N = 64)        = packed Toeplitz weights, rows 0..31 = hi(w[f][i-j]) (row = 4f + j), rows 32..63 = lo.
+//   D (TMEM, 64 cols) = x_hi * [w_hi | w_lo]  (N = 64)  +  x_lo * w_hi  (N = 32, accumulated into cols 0..31);
+//                       the epilogue adds column n and n + 32.
+// Roles (7 warps): warps 0-3 epilogue (TMEM lanes 32w..32w+31 = cols), warp 4 issues the MMAs and loads the
+// weights with one bulk copy per model, warps 5-6 split x rows into the hi/lo ring.  Two CTAs per SM keep the
+// tensor pipe busy across each other's per-MMA latency (tc_common.cuh).
+// =============================================================================================
+namespace {
+
+constexpr int TCF_THREADS = 224;
+constexpr int TCF_STAGES = 4;
+constexpr int TCF_F1 = 8;
+constexpr int TCF_WROW = 512;   // floats per k-step block of packed weights: 64 rows x 8
+
+__host__ __device__ inline int tcf_ksteps(int K1) { return (K1 + 3 + 7) / 8; }
+__host__ __device__ inline int tcf_xs_len(int K1, int T) {
+    int need = 4 * 127 + 8 * tcf_ksteps(K1);           // highest element any MMA row touches, + 1
+    int have = (K1 - 1) / 2 + T;
+    int n = need > have ? need : have;
+    return (n + 3) / 4 * 4;
+}
+
+// Packs the Toeplitz weight operand of every model: out[m][ks][n/8][k/4][n%8][k%4], n = 4f + j (+32 for lo).
+__global__ void tconv_wt_pack_kernel(const float *__restrict__ params, int64_t pstride, int64_t oW1, int K1,
+                                     int ksteps, float *__restrict__ out) {
+    const int m = blockIdx.y, ks = blockIdx.x, idx = threadIdx.x;      // 512 threads
+    const int n = idx >> 3, kk = idx & 7;
+    const int r = n & 31, f = r >> 2, j = r & 3;
+    const int k = ks * 8 + kk - j;
+    float w = (k >= 0 && k < K1) ? params[(int64_t)m * pstride + oW1 + f * K1 + k] : 0.f;
+    float hi, lo;
+    tc::split_tf32(w, hi, lo);
+    out[((int64_t)m * ksteps + ks) * TCF_WROW + (n >> 3) * 64 + (kk >> 2) * 32 + (n & 7) * 4 + (kk & 3)] =
+        n < 32 ? hi : lo;
+}
+
+__global__ void __launch_bounds__(TCF_THREADS, 2)
+tconv_fwd_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
+                    const float *__restrict__ wt_packed, float *__restrict__ y1, float *__restrict__ part,
+                    int n_rows, int B, int C, int T, int padl, int ksteps, int xs_len) {
+    extern __shared__ __align__(128) float smem[];
+    float *wt = smem;                                  // [ksteps][512]
+    float *xbuf = smem + (size_t)ksteps * TCF_WROW;    // [STAGES][2][xs_len]
+    __shared__ uint64_t bar_xfull[TCF_STAGES], bar_xempty[TCF_STAGES], bar_accfull[2], bar_accempty[2], bar_w,
+        bar_wfree;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row_lo = (int)((int64_t)n_rows * blockIdx.x / gridDim.x);
+    const int row_hi = (int)((int64_t)n_rows * (blockIdx.x + 1) / gridDim.x);
+    const int nrows = row_hi - row_lo;
+    if (nrows <= 0) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < TCF_STAGES; ++s) { tc::mbar_init(&bar_xfull[s], 1); tc::mbar_init(&bar_xempty[s], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_accfull[b], 1); tc::mbar_init(&bar_accempty[b], 4); }
+        tc::mbar_init(&bar_w, 1);
+        tc::mbar_init(&bar_wfree, 1);
+        tc::mbar_init_fence();
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_slot, 128);
+    for (int i = tid; i < TCF_STAGES * 2 * xs_len; i += TCF_THREADS) xbuf[i] = 0.f;   // halos stay zero
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp >= 5) {
+        // ---------------- producers: x row -> tf32 hi / lo halves in the ring ----------------
+        for (int li = warp - 5; li < nrows; li += 2) {
+            const int s = li % TCF_STAGES, u = li / TCF_STAGES;
+            const int row = row_lo + li;
+            const int n = row / C, c = row - n * C;
+            const int64_t xrow = x_index ? (int64_t)x_index[n] : (int64_t)n;
+            const float *src = x + (xrow * C + c) * (int64_t)T;
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = lane + 32 * q;
+                v[q] = e < T ? __ldg(src + e) : 0.f;
+            }
+            if (u > 0) tc::mbar_wait(&bar_xempty[s], (u - 1) & 1);
+            float *hi = xbuf + (size_t)s * 2 * xs_len + padl;
+            float *lo = hi + xs_len;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int e = lane + 32 * q;
+                if (e < T) {
+                    float h, l;
+                    tc::split_tf32(v[q], h, l);
+                    hi[e] = h;
+                    lo[e] = l;
+                }
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_xfull[s]);
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const bool leader = tc::elect_one();
+        const uint32_t idesc64 = tc::idesc_tf32(128, 64, 0, 0), idesc32 = tc::idesc_tf32(128, 32, 0, 0);
+        const uint64_t bdesc0 = tc::smem_desc(tc::smem_u32(wt), 128, 256);
+        const uint32_t wbytes = (uint32_t)ksteps * TCF_WROW * 4;
+        int cur_m = -1;
+        uint32_t w_phase = 0, wfree_phase = 0;
+        for (int li = 0; li < nrows; ++li) {
+            const int row = row_lo + li;
+            const int m = (row / C) / B;
+            if (m != cur_m) {
+                if (cur_m >= 0) {      // every MMA that reads the old weights must have retired
+                    if (leader) tc::mma_commit(&bar_wfree);
+                    tc::mbar_wait(&bar_wfree, wfree_phase);
+                    wfree_phase ^= 1;
+                }
+                if (leader) {
+                    tc::mbar_expect_tx(&bar_w, wbytes);
+                    const float *src = wt_packed + (int64_t)m * ksteps * TCF_WROW;
+                    for (uint32_t off = 0; off < wbytes; off += 16384) {
+                        const uint32_t nb = wbytes - off < 16384 ? wbytes - off : 16384;
+                        tc::tma_load_1d(reinterpret_cast<char *>(wt) + off, reinterpret_cast<const char *>(src) + off,
+                                        nb, &bar_w);
+                    }
+                }
+                tc::mbar_wait(&bar_w, w_phase);
+                w_phase ^= 1;
+                cur_m = m;
+            }
+            const int s = li % TCF_STAGES, u = li / TCF_STAGES, b = li & 1, ub = li >> 1;
+            tc::mbar_wait(&bar_xfull[s], u & 1);
+            if (ub > 0) tc::mbar_wait(&bar_accempty[b], (ub - 1) & 1);
+            tc::tc_fence_after_sync();
+            if (leader) {
+                const float *xhi = xbuf + (size_t)s * 2 * xs_len;
+                uint64_t ahi = tc::smem_desc(tc::smem_u32(xhi), 16, 128);
+                uint64_t alo = tc::smem_desc(tc::smem_u32(xhi + xs_len), 16, 128);
+                uint64_t bd = bdesc0;
+                const uint32_t d = tmem + b * 64;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    tc::mma_tf32_ss(d, ahi, bd, idesc64, ks > 0 ? 1u : 0u);
+                    tc::mma_tf32_ss(d, alo, bd, idesc32, 1u);
+                    ahi += 2;      // 32 B: the next 8 taps
+                    alo += 2;
+                    bd += (TCF_WROW * 4) >> 4;
+                }
+                tc::mma_commit(&bar_xempty[s]);
+                tc::mma_commit(&bar_accfull[b]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> y1 (+ BatchNorm-1 partial sums) ----------------
+        const int col = warp * 32 + lane, t0 = 4 * col;
+        const bool valid = t0 < T;
+        for (int li = 0; li < nrows; ++li) {
+            const int b = li & 1, ub = li >> 1;
+            tc::mbar_wait(&bar_accfull[b], ub & 1);
+            tc::tc_fence_after_sync();
+            float v0[32], v1[32];
+            const uint32_t ta = tmem + ((uint32_t)(warp * 32) << 16) + b * 64;
+            tc::tmem_ld32(ta, v0);
+            tc::tmem_ld32(ta + 32, v1);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_accempty[b]);
+            const int row = row_lo + li;
+            const int n = row / C, c = row - n * C;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v0[q] += v1[q];
+            if (valid) {
+#pragma unroll
+                for (int f = 0; f < TCF_F1; ++f) {
+                    float *dst = y1 + (((int64_t)n * TCF_F1 + f) * C + c) * (int64_t)T + t0;
+                    *reinterpret_cast<float4 *>(dst) = make_float4(v0[4 * f], v0[4 * f + 1], v0[4 * f + 2], v0[4 * f + 3]);
+                }
+            }
+            if (part != nullptr) {
+                float *prow = part + ((int64_t)row * 4 + warp) * (2 * TCF_F1);
+#pragma unroll
+                for (int f = 0; f < TCF_F1; ++f) {
+                    float sm = 0.f, sq = 0.f;
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            sm += v0[4 * f + j];
+                            sq = fmaf(v0[4 * f + j], v0[4 * f + j], sq);
+                        }
+                    }
+                    sm = warp_sum(sm);
+                    sq = warp_sum(sq);
+                    if (lane == 0) { prow[2 * f] = sm; prow[2 * f + 1] = sq; }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 128);
+}
+
+bool tc_env_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("EAV_TCONV"); v = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : 1; }
+    return v != 0;
+}
+
+}  // namespace
+
+bool tconv_fwd_use_tc(const NetDims &d) {
+    if (!tc_env_enabled()) return false;
+    if (d.F1 != TCF_F1 || (d.T & 3) || d.T > 512 || d.T < 4) return false;
+    const size_t smem = ((size_t)tcf_ksteps(d.K1) * TCF_WROW + (size_t)TCF_STAGES * 2 * tcf_xs_len(d.K1, d.T)) * 4;
+    return smem <= 110 * 1024;
+}
+size_t tconv_fwd_tc_scratch_floats(const NetDims &d) {
+    return tconv_fwd_use_tc(d) ? (size_t)d.M * tcf_ksteps(d.K1) * TCF_WROW : 0;
+}
+int tconv_fwd_tc_rows_per_sample(const NetDims &d) { return d.C * 4; }
+
+int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
+                        float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st) {
+    EAV_REQUIRE(wt_scratch != nullptr, EAV_ERR_BAD_ARG, "tconv_fwd_tc: no weight scratch");
+    const int ksteps = tcf_ksteps(d.K1), xs_len = tcf_xs_len(d.K1, d.T);
+    tconv_wt_pack_kernel<<<dim3(ksteps, d.M), 512, 0, st>>>(params, d.pstride, d.oW1, d.K1, ksteps, wt_scratch);
+    EAV_CUDA_LAUNCH_CHECK("tconv_wt_pack");
+    const size_t smem = ((size_t)ksteps * TCF_WROW + (size_t)TCF_STAGES * 2 * xs_len) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        EAV_REQUIRE(e == cudaSuccess, (int)e, "tconv_fwd_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_rows = d.N * d.C;
+    int grid = 2 * sms;
+    if (grid > n_rows) grid = n_rows;
+    tconv_fwd_tc_kernel<<<grid, TCF_THREADS, smem, st>>>(x, x_index, wt_scratch, y1, part, n_rows, d.B, d.C, d.T,
+                                                         d.pad1l, ksteps, xs_len);
+    EAV_CUDA_LAUNCH_CHECK("tconv_fwd_tc");
+    if (part_rows) *part_rows = d.B * tconv_fwd_tc_rows_per_sample(d);
+    return 0;
+}
+
+}  // namespace eav
+
+extern "C" int eav_tc_probe(const float *image_dev, int image_floats, int M, int N, int ksteps, int reps, int n_acc,
+                            int a_off, int a_lbo, int a_sbo, int a_major, int a_step, int b_off, int b_lbo,
+                            int b_sbo, int b_major, int b_step, int a_bits, int b_bits, float *d_out_dev, long long *cycles_dev,
+                            void *stream) {
+    using namespace eav;
+    EAV_REQUIRE(image_dev && d_out_dev && cycles_dev, EAV_ERR_BAD_ARG, "eav_tc_probe: null pointer");
+    EAV_REQUIRE((M == 64 || M == 128) && N >= 32 && N <= 256 && N % 32 == 0 && ksteps >= 1 && reps >= 1 && n_acc >= 1 && n_acc * N <= 512,
+                EAV_ERR_BAD_ARG, "eav_tc_probe: M in {64,128}, N a multiple of 32 in [32,256]");
+    EAV_REQUIRE(image_floats >= 0 && (size_t)image_floats * 4 <= 200 * 1024, EAV_ERR_BAD_ARG,
+                "eav_tc_probe: image larger than 200 KB");
+    ProbeArgs a{image_floats, M, N, ksteps, reps, n_acc, a_off, a_lbo, a_sbo, a_major, a_step,
+                b_off, b_lbo, b_sbo, b_major, b_step, a_bits, b_bits};
+    size_t smem = (size_t)image_floats * 4 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    EAV_REQUIRE(e == cudaSuccess, (int)e, "eav_tc_probe: %s", cudaGetErrorString(e));
+    // EAV_TC_PROBE_GRID > 1 replicates the CTA (same inputs, same outputs) to time co-resident CTAs sharing a tensor core
+    const char *g = getenv("EAV_TC_PROBE_GRID");
+    const int grid = g ? atoi(g) : 1;
+    tc_probe_kernel<<<grid > 0 ? grid : 1, 128, smem, (cudaStream_t)stream>>>(image_dev, a, d_out_dev, cycles_dev);
+    EAV_CUDA_LAUNCH_CHECK("tc_probe");
+    return 0;
+}

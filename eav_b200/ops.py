@@ -222,6 +222,19 @@ def measure_fp32_peak(mode=0) -> float:
     return v.value
 
 
+def tc_probe(image, M, N, ksteps, reps, a, b, n_acc=1, a_bits=0, b_bits=0):
+    """Runs reps x ksteps tcgen05.mma.kind::tf32 on a shared-memory image (1-D fp32 CUDA tensor) with the
+    operand descriptors a, b = (byte offset, LBO, SBO, major, byte step per k).  Returns (D[128, N], cycles)."""
+    _lib.require_device()
+    _chk_cuda(image, torch.float32, "image")
+    d = torch.zeros(128, N, dtype=torch.float32, device=image.device)
+    cyc = torch.zeros(1, dtype=torch.int64, device=image.device)
+    _lib.check(_lib.load().eav_tc_probe(_ptr(image), image.numel(), M, N, ksteps, reps, n_acc, *[int(v) for v in a],
+                                        *[int(v) for v in b], int(a_bits), int(b_bits), _ptr(d), _ptr(cyc), _stream()), "eav_tc_probe")
+    torch.cuda.synchronize()
+    return d, int(cyc.item())
+
+
 # ---------------------------------------------------------------------------------------
 # preprocessing
 # ---------------------------------------------------------------------------------------

@@ -243,6 +243,18 @@ int eav_measure_fp32_peak_outer(double *tflops, void *stream);
  * register (constant bank); 3: same with Blackwell packed FFMA2 (fma.rn.f32x2). */
 int eav_measure_fp32_peak_mode(int mode, double *tflops, void *stream);
 
+/* Diagnostic for the tcgen05 path: runs reps x ksteps `tcgen05.mma.cta_group::1.kind::tf32` (M x N x 8 each) in one
+ * CTA on a caller-supplied shared-memory image (image_floats fp32 words, <= 200 KB) with caller-supplied no-swizzle
+ * operand descriptors {byte offset, LBO, SBO, major (0 = K, 1 = MN), byte advance per k-step}; a_bits / b_bits are
+ * OR-ed into bits [32,64) of the A / B descriptor (swizzle mode in bits 61..63, base offset in 49..51; 0 = no swizzle).  Returns the fp32
+ * accumulator tile d_out[128][N] (row = TMEM lane; of accumulator 0 when the MMAs rotate over n_acc > 1
+ * independent TMEM column ranges) and the SM cycles from first issue to completion.  Used by
+ * scripts/tc_probe.py and tests/test_gpu_tc.py to pin the operand address maps the tensor-core kernels rely on. */
+int eav_tc_probe(const float *image_dev, int image_floats, int M, int N, int ksteps, int reps, int n_acc,
+                 int a_off, int a_lbo, int a_sbo, int a_major, int a_step,
+                 int b_off, int b_lbo, int b_sbo, int b_major, int b_step, int a_bits, int b_bits,
+                 float *d_out_dev, long long *cycles_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
