@@ -907,6 +907,7 @@ static size_t tconv_dw_smem(int T) {
 static int tconv_rk(int K1) { return K1 <= 64 ? 2 : K1 <= 128 ? 4 : K1 <= 256 ? 8 : K1 <= 320 ? 10 : 16; }
 
 int tconv_dw_ctas_per_model(const NetDims &d) {
+    if (tconv_bwd_dw_use_tc(d)) return tconv_bwd_dw_tc_splits(d);
     // ~two full waves of resident CTAs (148 SMs x up to 3 CTAs) when the work allows it
     int64_t rows = (int64_t)d.B * d.C;
     static int per_sm = -1;
@@ -947,6 +948,11 @@ int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index
     EAV_REQUIRE(d.F1 == 8, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: F1=%d unsupported (only 8)", d.F1);
     EAV_REQUIRE(d.K1 <= 512, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: kernLength=%d > 512 unsupported", d.K1);
     const int cpm = tconv_dw_ctas_per_model(d);
+    if (tconv_bwd_dw_use_tc(d)) {   // tcgen05 path (tconv_tc.cu); EAV_TCONV=ffma selects the CUDA-core kernel below
+        int rc = launch_tconv_bwd_dw_tc(d, x, x_index, dz1, y1, bnf1, bnb1, part, cpm, st);
+        if (rc) return rc;
+        return launch_reduce_partials(part, cpm, (int64_t)d.F1 * d.K1, d.M, d.pstride, grads + d.oW1, st);
+    }
     int rc;
     switch (tconv_rk(d.K1)) {
         case 2: rc = launch_tconv_bwd_dw_rk<2>(d, x, x_index, dz1, y1, bnf1, bnb1, part, st, cpm); break;

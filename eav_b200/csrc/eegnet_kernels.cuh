@@ -69,6 +69,11 @@ int launch_tconv_bwd_dw(const NetDims &d, const float *x, const int32_t *x_index
                         const float *y1, const float4 *bnf1, const float4 *bnb1, float *part,
                         float *grads, cudaStream_t st);
 
+bool tconv_bwd_dw_use_tc(const NetDims &d);
+int tconv_bwd_dw_tc_splits(const NetDims &d);     // partial slabs per model written by the tensor-core kernel
+int launch_tconv_bwd_dw_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
+                           const float *y1, const float4 *bnf1, const float4 *bnb1, float *part, int S,
+                           cudaStream_t st);
 int tconv_fwd_rows_per_sample(const NetDims &d);   // BN1 partial rows per sample written by tconv_fwd
 int sepconv_fwd_rows_per_model(const NetDims &d);   // BN3 partial rows per model written by sepconv_fwd
 int dw_fwd_tiles(const NetDims &d);   // time tiles per (sample, filter) of dw_fwd == BN2 partial rows per sample

@@ -349,6 +349,296 @@ int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index
     return 0;
 }
 
+// =============================================================================================
+// Weight gradient of the temporal convolution on the tensor cores.
+//
+//   dW[f][k] = sum_{rows (b,c)} sum_t dy[f][t] * xs[t + k + DELTA],     xs[PADL + t] = x[t], DELTA = PADL - padl
+// With t = 32 q + j:   D'[i][(f,j)] = sum_rows sum_q xs[32 q + i] * dy[f][32 q + j]   and
+//                      dW[f][k]     = sum_{j<32} D'[k + j + DELTA][(f,j)].
+// Both operands are the RAW row buffers, MN-major with the 128B/32B-atom swizzle (the only MN-major mode tf32 has):
+//   A[i][q] = xs[32 q + i]    -> LBO 128 B (next 32 i), SBO 512 B (next 4 q); M tile mt starts 512 B further
+//   B[(f,j)][q] = dy[f][32q+j]-> LBO = row pitch 2048 B (next f), SBO 512 B
+// and one k-step (8 q = 256 samples) advances both start addresses by 1024 B.  The swizzle is a function of the
+// absolute shared-memory address (scripts/tc_decode.py), so the producers store element e at swz(base + 4 e).
+// D' (M = up to 384 rows in 3 tiles, N = 128 = 4 filters x 32) stays in TMEM for all rows of a work unit
+// (model, filter half, row range); the epilogue sums the 32 diagonals through shared memory.
+// Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-12 producers (BatchNorm-1 backward is applied to
+// dz1 while staging, then the tf32 hi/lo split).
+// =============================================================================================
+namespace {
+
+// One ring stage per producer warp: a warp then waits on every phase of its own stage's `empty` barrier in
+// order.  (With more warps than stages a warp could test a parity two phases ahead, which mbarrier parity
+// waits cannot distinguish from "already complete".)
+constexpr int TCW_PROD_WARPS = 6;
+constexpr int TCW_THREADS = (5 + TCW_PROD_WARPS) * 32;
+constexpr int TCW_STAGES = TCW_PROD_WARPS;
+constexpr int TCW_XS = 896;                       // floats per x buffer (>= 32*15 + 384), 3584 B
+constexpr int TCW_DYROW = 512;                    // floats per dy row
+constexpr int TCW_STAGE_FLOATS = 2 * TCW_XS + 2 * 4 * TCW_DYROW;   // x hi, x lo, dy hi[4], dy lo[4] = 23552 B
+constexpr int TCW_SP = 33;                        // pitch of the diagonal-sum staging
+
+__device__ __forceinline__ uint32_t swz128_32(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void split4(float4 v, float4 &h, float4 &l) {
+    tc::split_tf32(v.x, h.x, l.x);
+    tc::split_tf32(v.y, h.y, l.y);
+    tc::split_tf32(v.z, h.z, l.z);
+    tc::split_tf32(v.w, h.w, l.w);
+}
+__device__ __forceinline__ uint64_t desc_mn_sw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return tc::smem_desc(saddr, lbo, sbo) | ((uint64_t)1 << 61);     // layout_type 1 = SWIZZLE_128B_BASE32B
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(TCW_THREADS, 1)
+tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
+                       const float *__restrict__ dz1, const float *__restrict__ y1,
+                       const float4 *__restrict__ bnf1, const float4 *__restrict__ bnb1, int bn_train, int M, int B,
+                       int C, int T, int K1, int padl, int S, float *__restrict__ part) {
+    extern __shared__ __align__(1024) float smem[];
+    float *ring = smem;                                        // [STAGES][STAGE_FLOATS]
+    float *diag = smem + TCW_STAGES * TCW_STAGE_FLOATS;        // [384][33]
+    __shared__ uint64_t bar_full[TCW_STAGES], bar_empty[TCW_STAGES], bar_accfull, bar_accempty;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F1 = 8;
+    const int PADL = (padl + 3) & ~3, DELTA = PADL - padl;
+    const int mtiles = (K1 + 31 + DELTA + 127) / 128;
+    const int ksteps = (T + 255) / 256;
+    const int rows_m = B * C;
+    const int n_units = 2 * M * S;
+
+    if (tid == 0) {
+        for (int s = 0; s < TCW_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
+        tc::mbar_init(&bar_accfull, 1);
+        tc::mbar_init(&bar_accempty, 4);
+        tc::mbar_init_fence();
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
+    for (int i = tid; i < TCW_STAGES * TCW_STAGE_FLOATS; i += TCW_THREADS) ring[i] = 0.f;   // halos / tails stay zero
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    auto unit_rows = [&](int u, int &m, int &fg, int &r_lo, int &r_hi) {
+        fg = u & 1;
+        const int ms = u >> 1;
+        m = ms / S;
+        const int sp = ms - m * S;
+        r_lo = (int)((int64_t)rows_m * sp / S);
+        r_hi = (int)((int64_t)rows_m * (sp + 1) / S);
+    };
+
+    if (warp >= 5) {
+        // ---------------- producers ----------------
+        const int pw = warp - 5;
+        int g = 0;                                     // running row counter of this CTA (all units)
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int m, fg, r_lo, r_hi;
+            unit_rows(u, m, fg, r_lo, r_hi);
+            for (int r = r_lo; r < r_hi; ++r, ++g) {
+                if (g % TCW_PROD_WARPS != pw) continue;
+                const int s = g % TCW_STAGES, use = g / TCW_STAGES;
+                const int b = r / C, c = r - b * C;
+                const int64_t n = (int64_t)m * B + b;
+                const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
+                const float *xsrc = x + (xrow * C + c) * (int64_t)T;
+                float4 xv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = 4 * (lane + 32 * q);
+                    xv[q] = t < T ? *reinterpret_cast<const float4 *>(xsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (use > 0) tc::mbar_wait(&bar_empty[s], (use - 1) & 1);
+                const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int t = 4 * (lane + 32 * q);
+                    if (t < T) {
+                        float4 h, l;
+                        split4(xv[q], h, l);
+                        const uint32_t a = sbase + 4u * (uint32_t)(PADL + t);
+                        sts_f4(swz128_32(a), h);
+                        sts_f4(swz128_32(a + 4u * TCW_XS), l);
+                    }
+                }
+                const uint32_t dybase = sbase + 4u * 2 * TCW_XS;
+#pragma unroll
+                for (int fp = 0; fp < 4; fp += 2) {      // two filters at a time bounds the registers in flight
+                    float4 dzv[2][4], yv[2][4];
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int f = fg * 4 + fp + h2;
+                        const int64_t base = ((n * F1 + f) * C + c) * (int64_t)T;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int t = 4 * (lane + 32 * q);
+                            const bool act = t < T;
+                            dzv[h2][q] = act ? *reinterpret_cast<const float4 *>(dz1 + base + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (bn_train)
+                                yv[h2][q] = act ? *reinterpret_cast<const float4 *>(y1 + base + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int f = fg * 4 + fp + h2;
+                        const float4 kb = bnb1[(int64_t)m * F1 + f];
+                        const float4 kf = bnf1[(int64_t)m * F1 + f];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int t = 4 * (lane + 32 * q);
+                            if (t < T) {
+                                float4 o;
+                                if (bn_train) {
+                                    o.x = kb.x * (dzv[h2][q].x - kb.y - (yv[h2][q].x - kf.x) * kf.y * kb.z);
+                                    o.y = kb.x * (dzv[h2][q].y - kb.y - (yv[h2][q].y - kf.x) * kf.y * kb.z);
+                                    o.z = kb.x * (dzv[h2][q].z - kb.y - (yv[h2][q].z - kf.x) * kf.y * kb.z);
+                                    o.w = kb.x * (dzv[h2][q].w - kb.y - (yv[h2][q].w - kf.x) * kf.y * kb.z);
+                                } else {
+                                    o = make_float4(kb.x * dzv[h2][q].x, kb.x * dzv[h2][q].y, kb.x * dzv[h2][q].z, kb.x * dzv[h2][q].w);
+                                }
+                                float4 h, l;
+                                split4(o, h, l);
+                                const uint32_t a = dybase + 4u * (uint32_t)((fp + h2) * TCW_DYROW + t);
+                                sts_f4(swz128_32(a), h);
+                                sts_f4(swz128_32(a + 4u * 4 * TCW_DYROW), l);
+                            }
+                        }
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_full[s]);
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_tf32(128, 128, 1, 1);
+        int g = 0, nu = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+            int m, fg, r_lo, r_hi;
+            unit_rows(u, m, fg, r_lo, r_hi);
+            if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);     // epilogue drained the previous unit
+            for (int r = r_lo; r < r_hi; ++r, ++g) {
+                const int s = g % TCW_STAGES, use = g / TCW_STAGES;
+                tc::mbar_wait(&bar_full[s], use & 1);
+                tc::tc_fence_after_sync();
+                if (leader) {
+                    const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
+                    const uint32_t xhi = sbase, xlo = sbase + 4u * TCW_XS;
+                    const uint32_t dyhi = sbase + 4u * 2 * TCW_XS, dylo = dyhi + 4u * 4 * TCW_DYROW;
+                    const uint32_t first = (r == r_lo) ? 0u : 1u;
+                    for (int mt = 0; mt < mtiles; ++mt) {
+                        const uint32_t d = tmem + mt * 128;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t ao = mt * 512 + ks * 1024, bo = ks * 1024;
+                            const uint64_t ah = desc_mn_sw(xhi + ao, 128, 512), al = desc_mn_sw(xlo + ao, 128, 512);
+                            const uint64_t bh = desc_mn_sw(dyhi + bo, 4 * TCW_DYROW, 512);
+                            const uint64_t bl = desc_mn_sw(dylo + bo, 4 * TCW_DYROW, 512);
+                            tc::mma_tf32_ss(d, ah, bh, idesc, (ks > 0) ? 1u : first);
+                            tc::mma_tf32_ss(d, ah, bl, idesc, 1u);
+                            tc::mma_tf32_ss(d, al, bh, idesc, 1u);
+                        }
+                    }
+                    tc::mma_commit(&bar_empty[s]);
+                    if (r == r_hi - 1) tc::mma_commit(&bar_accfull);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- epilogue: D' -> diagonal sums -> partial dW ----------------
+        int nu = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+            int m, fg, r_lo, r_hi;
+            unit_rows(u, m, fg, r_lo, r_hi);
+            const int sp = (u >> 1) - m * S;
+            tc::mbar_wait(&bar_accfull, nu & 1);
+            tc::tc_fence_after_sync();
+            for (int fl = 0; fl < 4; ++fl) {
+                for (int mt = 0; mt < mtiles; ++mt) {
+                    float v[32];
+                    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * 128 + fl * 32, v);
+                    tc::tmem_ld_wait();
+                    float *drow = diag + (size_t)(mt * 128 + warp * 32 + lane) * TCW_SP;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) drow[j] = v[j];
+                }
+                if (fl == 3) {           // all TMEM reads of this unit are done: the next unit may accumulate
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_accempty);
+                }
+                epi_bar();
+                float *dst = part + (((int64_t)m * S + sp) * F1 + fg * 4 + fl) * K1;
+                for (int k = tid; k < K1; k += 128) {
+                    float acc = 0.f;
+                    const float *p = diag + (size_t)(k + DELTA) * TCW_SP;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc += p[j * (TCW_SP + 1)];
+                    dst[k] = acc;
+                }
+                epi_bar();
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool tconv_bwd_dw_use_tc(const NetDims &d) {
+    if (!tc_env_enabled()) return false;
+    const int delta = ((d.pad1l + 3) & ~3) - d.pad1l;
+    return d.F1 == 8 && (d.T & 3) == 0 && d.T >= 4 && d.T <= 512 && d.K1 + 31 + delta <= 384 && d.B * d.C >= 8;
+}
+
+// row ranges per model: minimises  waves * (rows per unit * MMA time + epilogue)  over the split count
+int tconv_bwd_dw_tc_splits(const NetDims &d) {
+    const int rows = d.B * d.C;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int S = 1; S <= 128 && S * 8 <= rows; ++S) {
+        const int64_t units = 2ll * d.M * S;
+        const double waves = (double)((units + 147) / 148);
+        const double cost = waves * ((double)((rows + S - 1) / S) * 1152.0 + 12000.0);
+        if (cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
+int launch_tconv_bwd_dw_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
+                           const float *y1, const float4 *bnf1, const float4 *bnb1, float *part, int S,
+                           cudaStream_t st) {
+    const size_t smem = ((size_t)TCW_STAGES * TCW_STAGE_FLOATS + 384 * TCW_SP) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tconv_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        EAV_REQUIRE(e == cudaSuccess, (int)e, "tconv_bwd_dw_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int units = 2 * d.M * S;
+    const int grid = units < sms ? units : sms;
+    tconv_bwd_dw_tc_kernel<<<grid, TCW_THREADS, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train, d.M, d.B, d.C,
+                                                            d.T, d.K1, d.pad1l, S, part);
+    EAV_CUDA_LAUNCH_CHECK("tconv_bwd_dw_tc");
+    return 0;
+}
+
 }  // namespace eav
 
 extern "C" int eav_tc_probe(const float *image_dev, int image_floats, int M, int N, int ksteps, int reps, int n_acc,
