@@ -417,31 +417,69 @@ def main():
             torch.cuda.synchronize()
             stages[name] = a.elapsed_time(b) / reps
         tot = sum(stages.values())
-        dom = max(("tconv_fwd", "tconv_bwd_dw"), key=lambda k: stages[k])
-        peak = ops.measure_fp32_peak()
-        peak_outer = ops.measure_fp32_peak(1)
-        peak_ffma2 = ops.measure_fp32_peak(3)
-        ach = TCONV_FLOP_PER_SAMPLE * M * B / (stages[dom] * 1e-3) / 1e12
+        N = M * B
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 7700.0)
+        # dense tf32 runs at half the bf16 rate on tcgen05 (kind::tf32 consumes K=8 per 32 B, kind::f16 K=16)
+        tf32_peak = peaks.get("bf16_tflops", 2250.0) / 2
+        peak_src_t = ("MEASURED_PEAKS.json bf16_tflops (burst) / 2: dense tf32 peak of tcgen05" if peaks else
+                      "fallback: nominal 2250 TF/s bf16 / 2")
+        fp32_peak = ops.measure_fp32_peak()
+        fp32_ffma2 = ops.measure_fp32_peak(3)
+        tc_on = os.environ.get("EAV_TCONV", "") not in ("ffma", "0")
+        conv2 = 2.0 * 64 * 64 * 16 * 125           # block-2 (1,16) conv, flops per sample
+        # algorithmic work of each hot kernel, per launch
+        model = {
+            "tconv_fwd": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
+            "tconv_bwd_dw": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
+            "sepconv_fwd": ("fp32", conv2 * N, "flop"),
+            "sepconv_bwd_dx": ("fp32", conv2 * N, "flop"),
+            "sepconv_bwd_dw": ("fp32", conv2 * N, "flop"),
+            # y1 + dz1 (8x30x500 each) + y2 + dz2 (64x500 each), fp32
+            "dw_bwd": ("hbm", 4.0 * N * (2 * 8 * 30 * 500 + 2 * 64 * 500), "byte"),
+            # y1 read + y2 write
+            "dw_fwd": ("hbm", 4.0 * N * (8 * 30 * 500 + 64 * 500), "byte"),
+        }
+
+        def kernel_roofline(name):
+            bound, work, kind = model[name]
+            t = stages[name] * 1e-3
+            if kind == "flop":
+                ach, unit = work / t / 1e12, "TFLOP/s"
+                pk = tf32_peak if bound == "tensor" else fp32_peak
+            else:
+                ach, unit = work / t / 1e9, "GB/s"
+                pk = hbm_peak
+            return {"kernel": name, "bound": bound, "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk,
+                    "ms_per_launch": stages[name], "share_of_step": stages[name] / tot,
+                    ("algorithmic_flops_per_launch" if kind == "flop" else "algorithmic_bytes_per_launch"): work}
+
+        per_kernel = {k: kernel_roofline(k) for k in model}
+        dom = max(model, key=lambda k: stages[k])
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
         except Exception:
             pass
-        roof = {"bound": "fp32", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": traffic, "ms_per_launch": stages[dom], "share_of_step": stages[dom] / tot,
-                "peak_source": "measured live: register-resident FFMA loop on all SMs (eav_measure_fp32_peak); "
-                               "nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s. MEASURED_PEAKS.json holds "
-                               "only HBM and bf16-tensor peaks; this kernel runs on the fp32 CUDA cores by design "
-                               "(1e-4 parity budget rules out TF32, north_star)",
-                "ceilings": {"register_outer_product_ffma": peak_outer, "register_outer_product_ffma2": peak_ffma2,
-                             "frac_of_ffma2_ceiling": ach / peak_ffma2,
-                             "note": "same device, 8x8 register outer product (the instruction mix of a register-blocked "
-                                     "convolution): scalar FFMA with three register operands, and Blackwell packed FFMA2 "
-                                     "(fma.rn.f32x2), which both conv kernels use.  The register file, not the FMA pipe, "
-                                     "caps these forms; `peak` is the pipe peak (immediate-operand FFMA)"},
-                "algorithmic_flops_per_launch": TCONV_FLOP_PER_SAMPLE * M * B,
-                "whole_step": {"achieved": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                               "frac": FLOP_PER_SAMPLE * M * B / (ms * 1e-3) / 1e12 / peak}}
+        roof = dict(per_kernel[dom])
+        roof["traffic"] = traffic
+        roof["peak_source"] = {
+            "tensor": peak_src_t + ".  `achieved` counts the algorithmic conv flops (2*K1*F1*Chans*Samples per sample) "
+                      "once; the kernel issues 3 tf32 MMAs per product (hi*hi + hi*lo + lo*hi keeps fp32 parity) and "
+                      "its small-N tiles are bound by shared-memory operand reads, see DESIGN.md section 4.6",
+            "fp32": "measured live: register-resident FFMA loop on all SMs (eav_measure_fp32_peak)",
+            "hbm": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 7.7 TB/s nominal",
+        }[roof["bound"]]
+        roof["kernels"] = per_kernel
+        roof["fp32_ceilings"] = {"ffma_pipe_peak": fp32_peak, "register_outer_product_ffma2": fp32_ffma2,
+                                 "note": "CUDA-core ceilings on this device: immediate-operand FFMA loop, and an 8x8 "
+                                         "register outer product with packed FFMA2 (the block-2 conv kernels' mix)"}
+        roof["whole_step"] = {"achieved": FLOP_PER_SAMPLE * N / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                              "note": "algorithmic conv/dense flops of fwd+bwd over the measured step time"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -472,7 +510,12 @@ def main():
                        "bn_mode": args.bn_mode, "dropout": "on-device Philox" if head_train else "off (eval)",
                        "l2": "no explicit flush: a step streams ~3.5 GB of activations through a 126 MB L2, inputs "
                              "(80 MB batch gathered by index from a 0.7 GB resident set) exceed L2",
-                       "parallelism": f"subject-sharded x{world}, no collective", "cuda_graph": True},
+                       "parallelism": f"subject-sharded x{world}, no collective", "cuda_graph": True,
+                       "arithmetic": "fp32 storage and accumulation everywhere; the temporal conv (fwd and dW) runs on "
+                                     "tcgen05 as a 3-product tf32 split (hi*hi + hi*lo + lo*hi, ~2^-21 relative), "
+                                     "all other kernels on the fp32 CUDA cores"
+                                     if os.environ.get("EAV_TCONV", "") not in ("ffma", "0") else
+                                     "fp32 CUDA cores everywhere (EAV_TCONV=ffma)"},
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             ("eval_bn_step" if head_train else "train_bn_step"): {"ms_per_step": other_ms,

@@ -302,9 +302,10 @@ tconv_fwd_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
 }
 
 bool tc_env_enabled() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("EAV_TCONV"); v = (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) ? 0 : 1; }
-    return v != 0;
+    // read on every call: the choice also fixes the workspace layout, so it must not change between
+    // eav_eegnet_workspace_bytes and the launches of one engine (tests flip it between engines)
+    const char *e = getenv("EAV_TCONV");
+    return !(e && (!strcmp(e, "ffma") || !strcmp(e, "0")));
 }
 
 }  // namespace

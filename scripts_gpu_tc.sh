@@ -1,4 +1,6 @@
 #!/bin/bash
-# tensor-core temporal conv: parity tests, then stage timings for both paths
-timeout 300 python -m pytest tests/test_gpu_eegnet.py -m gpu -x -q 2>&1 | tail -15
-echo "== kbench tc"; timeout 100 python scripts/kbench.py --stages tconv_fwd,tconv_bwd_dw 2>&1 | tail -4
+echo "== kbench all stages in order (tc)"; timeout 100 python scripts/kbench.py --stages pool1_bwd,bn2_bwd_reduce,bn2_bwd_finalize,dw_bwd,bn1_bwd_finalize,tconv_bwd_dw,dw_bwd 2>&1 | tail -8
+echo "== bench ffma"; EAV_TCONV=ffma timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], {k:round(v,3) for k,v in d['stage_ms'].items() if v>0.05})"
+echo "== bench tc"; timeout 300 python bench.py --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], {k:round(v,3) for k,v in d['stage_ms'].items() if v>0.05})"
