@@ -97,6 +97,7 @@ WsLayout make_ws_layout(const NetDims &d) {
     pa = max_sz(pa, N * tconv_fwd_rows_per_sample(d) * 2 * d.F1);         // tconv_fwd
     pa = max_sz(pa, N * cdiv(d.T, 128) * 2 * d.G);                        // dw_fwd
     pa = max_sz(pa, (size_t)d.M * d.B * cdiv(d.T4, 128) * 2 * d.F2);       // sepconv_fwd (<= one row per sample and tile)
+    if (d.variant == EAV_VARIANT_TOR) pa = max_sz(pa, (size_t)d.M * sepconv_fwd_rows_per_model(d) * 2 * d.F2);
     pa = max_sz(pa, N * 2 * d.F2);                                        // pw_fwd / tail_bwd
     pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
     pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
@@ -112,6 +113,7 @@ WsLayout make_ws_layout(const NetDims &d) {
     w.dz2 = take(N * d.G * d.T);
     w.dz1 = take(N * d.F1 * d.C * d.T);
     w.tcw = take(tconv_fwd_tc_scratch_floats(d));
+    w.tcw2 = take(sepconv_tc_scratch_floats(d));
     w.total = o;
     return w;
 }
@@ -249,7 +251,7 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_BN2: return launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, dp_bn ? sums(2, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st);
         case ST_POOL1_FWD: return launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.d1), st);
         case ST_SEPCONV_FWD:
-            if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3), pstat, nullptr, st);
+            if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.tcw2), WS(float, w.y3), pstat, nullptr, st);
             TRY(launch_dwt_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3d), st));
             return launch_pw_fwd(d, WS(float, w.y3d), a.params, WS(float, w.y3), pstat, nullptr, st);
         case ST_BN3: return launch_bn_finalize(d, 3, part, rows3, W * d.B * d.T4, dp_bn ? sums(3, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf3), st);
@@ -271,7 +273,7 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_SEPCONV_BWD_DX:
             if (tor)
                 return launch_sepconv_bwd_dx(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3),
-                                             a.params, WS(float, w.dd1), st);
+                                             a.params, WS(float, w.tcw2), WS(float, w.dd1), st);
             return launch_pw_bwd(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), WS(float, w.y3d),
                                  a.params, WS(float, w.dy3d), partw3, a.grads, st);
         case ST_SEPCONV_BWD_DW:

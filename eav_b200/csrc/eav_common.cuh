@@ -122,6 +122,7 @@ struct WsLayout {
                                                        // dW3 kernels can run on a forked stream
     size_t dz3, dd1, dy3d, dz2, dz1;                   // backward scratch
     size_t tcw;                                        // packed tensor-core operand of the temporal conv weights
+    size_t tcw2;                                       // ... of the block-2 conv weights (forward pack, d(input) pack)
     size_t total;
 };
 WsLayout make_ws_layout(const NetDims &d);

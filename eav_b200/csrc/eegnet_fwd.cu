@@ -717,6 +717,7 @@ static SepPlan sepconv_plan(const NetDims &d, int ctas_xy) {
     return {pairs, singles};
 }
 int sepconv_fwd_rows_per_model(const NetDims &d) {
+    if (sepconv_use_tc(d)) return sepconv_tc_rows_per_model(d);
     SepPlan p = sepconv_plan(d, cdiv(d.T4, SC_UT) * cdiv(d.F2, SC_CO));
     return (p.pairs_per_model + p.singles_per_model) * cdiv(d.T4, SC_UT);
 }
@@ -725,8 +726,9 @@ static size_t sepconv_smem(int Cin) {
     return (size_t)(2 * SC_GC * SC_CO * SC_K + SC_SC * Cin * SC_XS) * sizeof(float);
 }
 
-int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *y3,
+int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *wt_scratch, float *y3,
                        float *part, int *part_rows, cudaStream_t st) {
+    if (sepconv_use_tc(d)) return launch_sepconv_tc(d, 0, d1, params, wt_scratch, y3, part, part_rows, st);
     EAV_REQUIRE(d.K2 == SC_K, EAV_ERR_UNSUPPORTED, "sepconv: kernel length %d unsupported (only 16)", d.K2);
     size_t smem = sepconv_smem(d.G);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv: F1*D=%d too large", d.G);
@@ -747,7 +749,8 @@ int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, f
 }
 
 int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
-                          const float4 *bnb3, const float *params, float *dd1, cudaStream_t st) {
+                          const float4 *bnb3, const float *params, float *wt_scratch, float *dd1, cudaStream_t st) {
+    if (sepconv_use_tc(d)) return launch_sepconv_tc(d, 1, dz3, params, wt_scratch, dd1, nullptr, nullptr, st);
     size_t smem = sepconv_smem(d.F2);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv_dx: F2=%d too large", d.F2);
     static bool attr_set = false;

@@ -11,6 +11,13 @@ namespace eav {
 // when that is 0)
 int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
                      float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st);
+bool tc_path_enabled(const char *var);   // false when EAV_TC or <var> is "ffma" / "0"
+// tensor-core (tcgen05) block-2 convolution, sepconv_tc.cu (mode 0 forward, 1 input gradient)
+bool sepconv_use_tc(const NetDims &d);
+size_t sepconv_tc_scratch_floats(const NetDims &d);
+int sepconv_tc_rows_per_model(const NetDims &d);
+int launch_sepconv_tc(const NetDims &d, int mode, const float *in, const float *params, float *wt_scratch, float *out,
+                      float *part, int *part_rows, cudaStream_t st);
 // tensor-core (tcgen05) variant of the temporal convolution, tconv_tc.cu
 bool tconv_fwd_use_tc(const NetDims &d);
 size_t tconv_fwd_tc_scratch_floats(const NetDims &d);
@@ -31,7 +38,7 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
 int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const uint8_t *mask1,
                      float *d1, cudaStream_t st);
 // M6: (1,K2) 'same' conv over G channels (variant 0) -> y3 raw [N][F2][T4] (+ BN3 partials)
-int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *y3,
+int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, float *wt_scratch, float *y3,
                        float *part, int *part_rows, cudaStream_t st);
 // variant 1 block 2: depthwise temporal conv + pointwise conv (CNN_EEG.py:35-37)
 int launch_dwt_fwd(const NetDims &d, const float *d1, const float *params, float *y3d, cudaStream_t st);
@@ -52,7 +59,7 @@ int launch_bn_bwd_finalize(const NetDims &d, int layer, const float *part, int r
 int launch_bn_bwd_apply(const NetDims &d, float *dz3, const float *y3, const float4 *bnf3, const float4 *bnb3,
                         cudaStream_t st);
 int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
-                          const float4 *bnb3, const float *params, float *dd1, cudaStream_t st);
+                          const float4 *bnb3, const float *params, float *wt_scratch, float *dd1, cudaStream_t st);
 int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,
                           const float4 *bnb3, const float *d1, float *part, float *grads, cudaStream_t st);
 int launch_pw_bwd(const NetDims &d, const float *dz3, const float *y3, const float4 *bnf3,

@@ -301,14 +301,21 @@ tconv_fwd_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_i
     if (warp == 4) tc::tmem_dealloc(tmem, 128);
 }
 
-bool tc_env_enabled() {
-    // read on every call: the choice also fixes the workspace layout, so it must not change between
-    // eav_eegnet_workspace_bytes and the launches of one engine (tests flip it between engines)
-    const char *e = getenv("EAV_TCONV");
-    return !(e && (!strcmp(e, "ffma") || !strcmp(e, "0")));
-}
+bool tc_env_enabled() { return tc_path_enabled("EAV_TCONV"); }
 
 }  // namespace
+
+// EAV_TC=ffma switches every tensor-core path off, <var>=ffma one of them (A/B runs, tests).  Read on every call:
+// the choice also fixes the workspace layout, so it must not change between eav_eegnet_workspace_bytes and the
+// launches of one engine (tests flip it between engines).
+bool tc_path_enabled(const char *var) {
+    const char *names[2] = {"EAV_TC", var};
+    for (const char *nm : names) {
+        const char *e = getenv(nm);
+        if (e && (!strcmp(e, "ffma") || !strcmp(e, "0"))) return false;
+    }
+    return true;
+}
 
 bool tconv_fwd_use_tc(const NetDims &d) {
     if (!tc_env_enabled()) return false;

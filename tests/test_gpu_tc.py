@@ -1,6 +1,6 @@
 """-m gpu tests of the tcgen05 path of the temporal convolution (eav_b200/csrc/tconv_tc.cu):
  * the shared-memory operand address maps the kernels rely on, decoded on the device (eav_tc_probe);
- * the tensor-core kernels against the CUDA-core kernels (EAV_TCONV=ffma) on the same inputs, for the
+ * the tensor-core kernels against the CUDA-core kernels (EAV_TC=ffma) on the same inputs, for the
    reference shape (EEGNet_tor.py:145: Chans=30, Samples=500, kernLength=300) and for other shapes that
    change the number of k-steps / M tiles.
 Parity with the reference itself is in test_gpu_eegnet.py (which runs the tensor-core path by default)."""
@@ -60,8 +60,8 @@ def test_probe_mn_major_swizzled_operand(as_a, off, lbo, sbo):
 
 def _run(dims, M, B, x, y, params, bn, train, m1, m2, mode):
     from eav_b200.ops import EegnetEngine
-    old = os.environ.get("EAV_TCONV")
-    os.environ["EAV_TCONV"] = mode
+    old = os.environ.get("EAV_TC")
+    os.environ["EAV_TC"] = mode
     try:
         eng = EegnetEngine(dims, M, B)
         p, b = params.clone(), bn.clone()
@@ -72,9 +72,9 @@ def _run(dims, M, B, x, y, params, bn, train, m1, m2, mode):
         return out.clone(), eng.saved("y1").clone(), grads.clone(), b.clone()
     finally:
         if old is None:
-            os.environ.pop("EAV_TCONV", None)
+            os.environ.pop("EAV_TC", None)
         else:
-            os.environ["EAV_TCONV"] = old
+            os.environ["EAV_TC"] = old
 
 
 @pytest.mark.parametrize("shape", [
