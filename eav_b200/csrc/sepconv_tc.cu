@@ -13,7 +13,7 @@
 //   D[:, 0:128] = a_hi * [w_hi | w_lo]   (N = 128)     D[:, 0:64] += a_lo * w_hi   (N = 64);  out = D[:, o] + D[:, 64+o].
 // The packed weights of one model are 512 KB (hi and lo), more than shared memory: they are streamed from L2
 // through a TMA ring while TWO samples (both resident in shared memory) consume every block.
-// Roles: warps 0-3 epilogue, warp 4 MMA issue, warp 5 weight TMA, warps 6-9 activation producers.
+// Roles: warps 0-3 epilogue, warp 4 MMA issue, warp 5 weight TMA, warps 6-13 activation producers.
 #include <cstdlib>
 #include <cstring>
 
@@ -24,7 +24,8 @@
 namespace eav {
 namespace {
 
-constexpr int SCT_THREADS = 320;
+constexpr int SCT_PROD_WARPS = 8;         // 16 four-channel chunks / 2 per warp
+constexpr int SCT_THREADS = (6 + SCT_PROD_WARPS) * 32;
 constexpr int SCT_C = 64;                 // input channels == output channels
 constexpr int SCT_K = 16;                 // taps
 constexpr int SCT_ROWS = 144;             // activation rows: 128 positions + 16 taps
@@ -74,7 +75,7 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
 
     if (tid == 0) {
         for (int s = 0; s < SCT_WSTAGES; ++s) { tc::mbar_init(&bar_wfull[s], 1); tc::mbar_init(&bar_wempty[s], 1); }
-        tc::mbar_init(&bar_actfull, 4);
+        tc::mbar_init(&bar_actfull, SCT_PROD_WARPS);
         tc::mbar_init(&bar_actempty, 1);
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_accfull[b], 1); tc::mbar_init(&bar_accempty[b], 4); }
         tc::mbar_init_fence();
@@ -96,29 +97,49 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
 
     if (warp >= 6) {
         // ---------------- activation producers: [c][u] rows -> channel-interleaved hi / lo ----------------
+        // The global loads of pair lp are issued BEFORE waiting for the MMAs of pair lp-1 to release the
+        // buffers, so only the split + shared-memory stores sit between two pairs' MMA streams.
         const int pw = warp - 6;
         for (int lp = 0; lp < np; ++lp) {
             int m, n0, cnt;
             pair_samples(p_lo + lp, m, n0, cnt);
-            if (lp > 0) tc::mbar_wait(&bar_actempty, (lp - 1) & 1);
-            for (int s = 0; s < cnt; ++s) {
-                const float *src = in + (int64_t)(n0 + s) * SCT_C * U;
-                float *hi = act + (size_t)s * 2 * SCT_ACT, *lo = hi + SCT_ACT;
-                for (int c4 = pw; c4 < 16; c4 += 4) {
-                    const float *r0 = src + (int64_t)(4 * c4) * U;
+            float4 v[2][2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float *src = in + (int64_t)(n0 + (s < cnt ? s : 0)) * SCT_C * U;
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    const float *r0 = src + (int64_t)(4 * (pw + SCT_PROD_WARPS * ci)) * U;
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int u = lane + 32 * it;
-                        if (u < U) {
-                            float4 v = make_float4(r0[u], r0[U + u], r0[2 * U + u], r0[3 * U + u]);
-                            float4 h, l;
-                            tc::split_tf32(v.x, h.x, l.x);
-                            tc::split_tf32(v.y, h.y, l.y);
-                            tc::split_tf32(v.z, h.z, l.z);
-                            tc::split_tf32(v.w, h.w, l.w);
-                            const int o = c4 * SCT_CHUNK + (u + PL) * 4;
-                            *reinterpret_cast<float4 *>(hi + o) = h;
-                            *reinterpret_cast<float4 *>(lo + o) = l;
+                        v[s][ci][it] = u < U ? make_float4(__ldg(r0 + u), __ldg(r0 + U + u), __ldg(r0 + 2 * U + u),
+                                                           __ldg(r0 + 3 * U + u))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            if (lp > 0) tc::mbar_wait(&bar_actempty, (lp - 1) & 1);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s < cnt) {
+                    float *hi = act + (size_t)s * 2 * SCT_ACT, *lo = hi + SCT_ACT;
+#pragma unroll
+                    for (int ci = 0; ci < 2; ++ci) {
+                        const int c4 = pw + SCT_PROD_WARPS * ci;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int u = lane + 32 * it;
+                            if (u < U) {
+                                float4 h, l;
+                                tc::split_tf32(v[s][ci][it].x, h.x, l.x);
+                                tc::split_tf32(v[s][ci][it].y, h.y, l.y);
+                                tc::split_tf32(v[s][ci][it].z, h.z, l.z);
+                                tc::split_tf32(v[s][ci][it].w, h.w, l.w);
+                                const int o = c4 * SCT_CHUNK + (u + PL) * 4;
+                                *reinterpret_cast<float4 *>(hi + o) = h;
+                                *reinterpret_cast<float4 *>(lo + o) = l;
+                            }
                         }
                     }
                 }
