@@ -294,6 +294,7 @@ int launch_bn_bwd_apply(const NetDims &d, float *dz3, const float *y3, const flo
 }
 
 int sepconv_dw_splits(const NetDims &d) {
+    if (sepconv_use_tc(d)) return sepconv_dw_tc_splits(d);
     // Split the batch into `s` groups: CTAs = M * ceil(G/16) * s, each walking ceil(B/s) samples.
     const int per_model = cdiv(d.G, SW_GC);
     const int slots = 148 * 2;
@@ -311,6 +312,8 @@ int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, c
     EAV_REQUIRE(d.F2 % 8 == 0 && d.F2 <= 64, EAV_ERR_UNSUPPORTED, "sepconv_dw: F2=%d unsupported (multiple of 8, <= 64)", d.F2);
     EAV_REQUIRE(d.K2 == 16, EAV_ERR_UNSUPPORTED, "sepconv_dw: kernel length %d unsupported", d.K2);
     const int splits = sepconv_dw_splits(d);
+    if (sepconv_use_tc(d))      // tcgen05 path (sepconv_tc.cu); dz3 already holds dy3 (bn_bwd_apply stage)
+        return launch_sepconv_dw_tc(d, dz3, d1, part, grads, splits, st);
     size_t smem = (size_t)2 * (d.F2 * SW_UP + SW_GC * SW_XS) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {

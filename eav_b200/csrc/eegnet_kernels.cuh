@@ -18,6 +18,9 @@ size_t sepconv_tc_scratch_floats(const NetDims &d);
 int sepconv_tc_rows_per_model(const NetDims &d);
 int launch_sepconv_tc(const NetDims &d, int mode, const float *in, const float *params, float *wt_scratch, float *out,
                       float *part, int *part_rows, cudaStream_t st);
+int sepconv_dw_tc_splits(const NetDims &d);       // partial slabs per model written by the tensor-core dW3 kernel
+int launch_sepconv_dw_tc(const NetDims &d, const float *dy3, const float *d1, float *part, float *grads, int S,
+                         cudaStream_t st);
 // tensor-core (tcgen05) variant of the temporal convolution, tconv_tc.cu
 bool tconv_fwd_use_tc(const NetDims &d);
 size_t tconv_fwd_tc_scratch_floats(const NetDims &d);

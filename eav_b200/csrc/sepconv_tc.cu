@@ -248,6 +248,215 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
     if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// Weight gradient of the block-2 conv on the tensor cores.
+//
+//   dW3[o][g][k] = sum_{samples} sum_u dy3[o][u] * d1[g][u + k - pad]
+// With k = 4 k4 + 2 sb + sa and u' = u + sa:
+//   D_k4[(sa,o)][(sb,g)] = sum_{u'} A[(sa,o)][u'] * B[(sb,g)][u' + 4 k4],
+//   A[(sa,o)][u'] = dy3[o][u' - sa],   B[(sb,g)][rho] = d1[g][rho + 2 sb - pad]
+// i.e. M = 128 = two row-shifted copies of dy3^T, N = 128 = two row-shifted copies of d1^T, K = positions, and the
+// four accumulators D_0..D_3 (4 x 128 columns = all of TMEM) hold the 16 taps.  Operands are MN-major
+// (rows = positions, 128 B = 32 channels per row, 128B/32B-atom swizzle); tap group k4 is a start-address shift of
+// 4 rows.  A whole sample (dy3 and d1, 32 KB each) is bulk-copied into a staging buffer; eight producer warps
+// transpose it 16 positions at a time (stride-U reads are conflict-free for odd U) into a 3-stage operand ring,
+// applying the tf32 hi/lo split.  One work unit = a range of samples of one model; D stays in TMEM over the unit.
+// =============================================================================================
+constexpr int SDW_R = 16;                           // positions per chunk
+constexpr int SDW_BROWS = SDW_R + 12;               // rows of the d1 operand a chunk touches (4 tap groups)
+constexpr int SDW_A = 4 * SDW_R * 32;               // floats, one of hi / lo
+constexpr int SDW_B = 4 * SDW_BROWS * 32;
+constexpr int SDW_STAGE = 2 * SDW_A + 2 * SDW_B;    // 11264 floats = 45056 B
+constexpr int SDW_STAGES = 3;
+constexpr int SDW_STG = 64 * 128;                   // staging floats per tensor (U <= 128)
+constexpr int SDW_PROD_WARPS = 8;
+constexpr int SDW_THREADS = (6 + SDW_PROD_WARPS) * 32;
+constexpr size_t SDW_SMEM = ((size_t)SDW_STAGES * SDW_STAGE + 2 * SDW_STG) * 4;    // 200704 B
+
+__device__ __forceinline__ uint32_t sdw_swz(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }
+__device__ __forceinline__ void sdw_sts(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t sdw_desc(uint32_t saddr, uint32_t lbo) {
+    return tc::smem_desc(saddr, lbo, 512) | ((uint64_t)1 << 61);     // MN-major, SWIZZLE_128B_BASE32B
+}
+
+__global__ void __launch_bounds__(SDW_THREADS, 1)
+sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1, float *__restrict__ part, int M,
+                     int B, int U, int pad, int S) {
+    extern __shared__ __align__(1024) float smem[];
+    float *ring = smem;                                   // [STAGES][A hi, A lo, B hi, B lo]
+    float *stg = smem + SDW_STAGES * SDW_STAGE;           // [dy3 sample][d1 sample]
+    __shared__ uint64_t bar_full[SDW_STAGES], bar_empty[SDW_STAGES], bar_stgfull, bar_stgempty, bar_accfull,
+        bar_accempty;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_units = M * S;
+    const int n_chunks = (U + 1 + SDW_R - 1) / SDW_R;
+
+    if (tid == 0) {
+        for (int s = 0; s < SDW_STAGES; ++s) { tc::mbar_init(&bar_full[s], SDW_PROD_WARPS); tc::mbar_init(&bar_empty[s], 1); }
+        tc::mbar_init(&bar_stgfull, 1);
+        tc::mbar_init(&bar_stgempty, SDW_PROD_WARPS);
+        tc::mbar_init(&bar_accfull, 1);
+        tc::mbar_init(&bar_accempty, 4);
+        tc::mbar_init_fence();
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    auto unit_range = [&](int u, int &m, int &b_lo, int &b_hi) {
+        m = u / S;
+        const int sp = u - m * S;
+        b_lo = (int)((int64_t)B * sp / S);
+        b_hi = (int)((int64_t)B * (sp + 1) / S);
+    };
+
+    if (warp >= 6) {
+        // ---------------- producers: staging [ch][u] -> transposed, swizzled, hi / lo operand chunks ----------------
+        const int pw = warp - 6;
+        const float *sdy = stg, *sd1 = stg + SDW_STG;
+        int g = 0, ns = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int m, b_lo, b_hi;
+            unit_range(u, m, b_lo, b_hi);
+            for (int b = b_lo; b < b_hi; ++b, ++ns) {
+                tc::mbar_wait(&bar_stgfull, ns & 1);
+                for (int c = 0; c < n_chunks; ++c, ++g) {
+                    const int st = g % SDW_STAGES, use = g / SDW_STAGES;
+                    if (use > 0) tc::mbar_wait(&bar_empty[st], (use - 1) & 1);
+                    const uint32_t base = tc::smem_u32(ring + (size_t)st * SDW_STAGE);
+                    for (int item = pw; item < 64 + 4 * SDW_BROWS; item += SDW_PROD_WARPS) {
+                        float v = 0.f;
+                        uint32_t a;
+                        if (item < 64) {          // dy3 operand: copy sa = item / 32, half h, row r
+                            const int sa = item >> 5, h = (item >> 4) & 1, r = item & 15;
+                            const int uu = c * SDW_R + r - sa;
+                            if (uu >= 0 && uu < U) v = sdy[(h * 32 + lane) * U + uu];
+                            a = base + (uint32_t)(((sa * 2 + h) * SDW_R + r) * 128 + lane * 4);
+                        } else {                  // d1 operand: copy sb, half h, row r
+                            const int ib = item - 64;
+                            const int sb = ib / (2 * SDW_BROWS), rem = ib - sb * 2 * SDW_BROWS;
+                            const int h = rem / SDW_BROWS, r = rem - h * SDW_BROWS;
+                            const int t = c * SDW_R + r + 2 * sb - pad;
+                            if (t >= 0 && t < U) v = sd1[(h * 32 + lane) * U + t];
+                            a = base + (uint32_t)(2 * SDW_A * 4 + ((sb * 2 + h) * SDW_BROWS + r) * 128 + lane * 4);
+                        }
+                        float hi, lo;
+                        tc::split_tf32(v, hi, lo);
+                        sdw_sts(sdw_swz(a), hi);
+                        sdw_sts(sdw_swz(a + (item < 64 ? SDW_A : SDW_B) * 4), lo);
+                    }
+                    tc::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_full[st]);
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_stgempty);     // this warp no longer reads the staged sample
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------- staging loads: one sample of dy3 and of d1 per bulk-copy pair ----------------
+        if (tc::elect_one()) {
+            const uint32_t bytes = (uint32_t)(64 * U * 4);
+            int ns = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int m, b_lo, b_hi;
+                unit_range(u, m, b_lo, b_hi);
+                for (int b = b_lo; b < b_hi; ++b, ++ns) {
+                    if (ns > 0) tc::mbar_wait(&bar_stgempty, (ns - 1) & 1);
+                    const int64_t n = (int64_t)m * B + b;
+                    tc::mbar_expect_tx(&bar_stgfull, 2 * bytes);
+                    tc::tma_load_1d(stg, dy3 + n * 64 * U, bytes, &bar_stgfull);
+                    tc::tma_load_1d(stg + SDW_STG, d1 + n * 64 * U, bytes, &bar_stgfull);
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- MMA issuer ----------------
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::idesc_tf32(128, 128, 1, 1);
+        int g = 0, nu = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+            int m, b_lo, b_hi;
+            unit_range(u, m, b_lo, b_hi);
+            if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);
+            const int total = (b_hi - b_lo) * n_chunks;
+            for (int ci = 0; ci < total; ++ci, ++g) {
+                const int st = g % SDW_STAGES, use = g / SDW_STAGES;
+                tc::mbar_wait(&bar_full[st], use & 1);
+                tc::tc_fence_after_sync();
+                if (leader) {
+                    const uint32_t base = tc::smem_u32(ring + (size_t)st * SDW_STAGE);
+                    const uint32_t a_hi = base, a_lo = base + SDW_A * 4;
+                    const uint32_t b_hi_ = base + 2 * SDW_A * 4, b_lo_ = b_hi_ + SDW_B * 4;
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint32_t ao = ks * 1024, bo = k4 * 512 + ks * 1024;
+                            const uint64_t ah = sdw_desc(a_hi + ao, SDW_R * 128), al = sdw_desc(a_lo + ao, SDW_R * 128);
+                            const uint64_t bh = sdw_desc(b_hi_ + bo, SDW_BROWS * 128), bl = sdw_desc(b_lo_ + bo, SDW_BROWS * 128);
+                            const uint32_t d = tmem + k4 * 128;
+                            tc::mma_tf32_ss(d, ah, bh, idesc, (ci > 0 || ks > 0) ? 1u : 0u);
+                            tc::mma_tf32_ss(d, ah, bl, idesc, 1u);
+                            tc::mma_tf32_ss(d, al, bh, idesc, 1u);
+                        }
+                    }
+                    tc::mma_commit(&bar_empty[st]);
+                    if (ci == total - 1) tc::mma_commit(&bar_accfull);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- epilogue: D_k4[(sa,o)][(sb,g)] -> part[unit][k][o][g] ----------------
+        int nu = 0;
+        const int m_idx = warp * 32 + lane;
+        const int sa = m_idx >> 6, o = m_idx & 63;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+            tc::mbar_wait(&bar_accfull, nu & 1);
+            tc::tc_fence_after_sync();
+            float *pu = part + (int64_t)u * 16 * 4096;
+#pragma unroll 1
+            for (int k4 = 0; k4 < 4; ++k4) {
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float v[32];
+                    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + k4 * 128 + q * 32, v);
+                    tc::tmem_ld_wait();
+                    const int k = 4 * k4 + 2 * (q >> 1) + sa;
+                    float4 *dst = reinterpret_cast<float4 *>(pu + ((int64_t)k * 64 + o) * 64 + (q & 1) * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_accempty);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+// grads[m][oW3 + (o*64 + g)*16 + k] = sum_s part[(m*S + s)][k][o][g]   (fixed order)
+__global__ void sepconv_dw_reduce_kernel(const float *__restrict__ part, int S, int64_t pstride, int64_t oW3,
+                                         float *__restrict__ grads) {
+    const int m = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (k, o, g), g fastest
+    if (i >= 16 * 4096) return;
+    const int g = i & 63, o = (i >> 6) & 63, k = i >> 12;
+    const float *p = part + (int64_t)m * S * 65536 + i;
+    float s = 0.f;
+    for (int j = 0; j < S; ++j) s += p[(int64_t)j * 65536];
+    grads[(int64_t)m * pstride + oW3 + (o * 64 + g) * 16 + k] = s;
+}
+
 }  // namespace
 
 bool sepconv_use_tc(const NetDims &d) {
@@ -285,6 +494,43 @@ int launch_sepconv_tc(const NetDims &d, int mode, const float *in, const float *
     sepconv_tc_kernel<<<grid, SCT_THREADS, SCT_SMEM, st>>>(in, wt, out, mode == 0 ? part : nullptr, d.M, d.B, d.T4, PL);
     EAV_CUDA_LAUNCH_CHECK(mode == 0 ? "sepconv_fwd_tc" : "sepconv_bwd_dx_tc");
     if (part_rows) *part_rows = sepconv_tc_rows_per_model(d);
+    return 0;
+}
+
+// sample ranges per model: minimises  waves * (samples per unit * MMA time + epilogue)
+int sepconv_dw_tc_splits(const NetDims &d) {
+    const int n_chunks = (d.T4 + 1 + SDW_R - 1) / SDW_R;
+    int best = 1;
+    double best_cost = 1e30;
+    for (int S = 1; S <= d.B && S <= 64; ++S) {
+        const int64_t units = (int64_t)d.M * S;
+        const double waves = (double)((units + 147) / 148);
+        const double cost = waves * ((double)((d.B + S - 1) / S) * n_chunks * 24 * 64.0 + 8000.0);
+        if (cost < best_cost) { best_cost = cost; best = S; }
+    }
+    return best;
+}
+
+int launch_sepconv_dw_tc(const NetDims &d, const float *dy3, const float *d1, float *part, float *grads, int S,
+                         cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(sepconv_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDW_SMEM);
+        EAV_REQUIRE(e == cudaSuccess, (int)e, "sepconv_dw_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int units = d.M * S;
+    sepconv_dw_tc_kernel<<<units < sms ? units : sms, SDW_THREADS, SDW_SMEM, st>>>(dy3, d1, part, d.M, d.B, d.T4,
+                                                                                   d.pad2l, S);
+    EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dw_tc");
+    sepconv_dw_reduce_kernel<<<dim3(65536 / 256, d.M), 256, 0, st>>>(part, S, d.pstride, d.oW3, grads);
+    EAV_CUDA_LAUNCH_CHECK("sepconv_dw_reduce");
     return 0;
 }
 
