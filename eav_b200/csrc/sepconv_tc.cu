@@ -259,7 +259,7 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
 // four accumulators D_0..D_3 (4 x 128 columns = all of TMEM) hold the 16 taps.  Operands are MN-major
 // (rows = positions, 128 B = 32 channels per row, 128B/32B-atom swizzle); tap group k4 is a start-address shift of
 // 4 rows.  A whole sample (dy3 and d1, 32 KB each) is bulk-copied into a staging buffer; eight producer warps
-// transpose it 16 positions at a time (stride-U reads are conflict-free for odd U) into a 3-stage operand ring,
+// transpose it 16 positions at a time (stride-U reads are conflict-free for odd U) into a 2-stage operand ring,
 // applying the tf32 hi/lo split.  One work unit = a range of samples of one model; D stays in TMEM over the unit.
 // =============================================================================================
 constexpr int SDW_R = 16;                           // positions per chunk
@@ -267,15 +267,15 @@ constexpr int SDW_BROWS = SDW_R + 12;               // rows of the d1 operand a 
 constexpr int SDW_A = 4 * SDW_R * 32;               // floats, one of hi / lo
 constexpr int SDW_B = 4 * SDW_BROWS * 32;
 constexpr int SDW_STAGE = 2 * SDW_A + 2 * SDW_B;    // 11264 floats = 45056 B
-constexpr int SDW_STAGES = 3;
+constexpr int SDW_STAGES = 2;
 constexpr int SDW_STG = 64 * 128;                   // staging floats per tensor (U <= 128)
 constexpr int SDW_PROD_WARPS = 8;
 constexpr int SDW_THREADS = (6 + SDW_PROD_WARPS) * 32;
-constexpr size_t SDW_SMEM = ((size_t)SDW_STAGES * SDW_STAGE + 2 * SDW_STG) * 4;    // 200704 B
+constexpr size_t SDW_SMEM = ((size_t)SDW_STAGES * SDW_STAGE + 4 * SDW_STG) * 4;    // 221184 B: ring + 2 staged samples
 
 __device__ __forceinline__ uint32_t sdw_swz(uint32_t a) { return a ^ (((a >> 7) & 3u) << 5); }
-__device__ __forceinline__ void sdw_sts(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+__device__ __forceinline__ void sdw_sts4(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ uint64_t sdw_desc(uint32_t saddr, uint32_t lbo) {
     return tc::smem_desc(saddr, lbo, 512) | ((uint64_t)1 << 61);     // MN-major, SWIZZLE_128B_BASE32B
@@ -286,8 +286,8 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
                      int B, int U, int pad, int S) {
     extern __shared__ __align__(1024) float smem[];
     float *ring = smem;                                   // [STAGES][A hi, A lo, B hi, B lo]
-    float *stg = smem + SDW_STAGES * SDW_STAGE;           // [dy3 sample][d1 sample]
-    __shared__ uint64_t bar_full[SDW_STAGES], bar_empty[SDW_STAGES], bar_stgfull, bar_stgempty, bar_accfull,
+    float *stg = smem + SDW_STAGES * SDW_STAGE;           // 2 x [dy3 sample][d1 sample]
+    __shared__ uint64_t bar_full[SDW_STAGES], bar_empty[SDW_STAGES], bar_stgfull[2], bar_stgempty[2], bar_accfull,
         bar_accempty;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -296,8 +296,7 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
 
     if (tid == 0) {
         for (int s = 0; s < SDW_STAGES; ++s) { tc::mbar_init(&bar_full[s], SDW_PROD_WARPS); tc::mbar_init(&bar_empty[s], 1); }
-        tc::mbar_init(&bar_stgfull, 1);
-        tc::mbar_init(&bar_stgempty, SDW_PROD_WARPS);
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&bar_stgfull[b], 1); tc::mbar_init(&bar_stgempty[b], SDW_PROD_WARPS); }
         tc::mbar_init(&bar_accfull, 1);
         tc::mbar_init(&bar_accempty, 4);
         tc::mbar_init_fence();
@@ -317,45 +316,63 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
 
     if (warp >= 6) {
         // ---------------- producers: staging [ch][u] -> transposed, swizzled, hi / lo operand chunks ----------------
+        // Item = (operand copy, channel half, 4 rows): lane (a = lane % 8, b = lane / 8) gathers channels 4a..4a+3 of
+        // row 4 rq + b from the staged [ch][u] sample (4 conflict-free LDS for odd U) and writes one 16-byte piece of
+        // the transposed row for each of hi / lo.
         const int pw = warp - 6;
-        const float *sdy = stg, *sd1 = stg + SDW_STG;
+        const int la = lane & 7, lb = lane >> 3;
         int g = 0, ns = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             int m, b_lo, b_hi;
             unit_range(u, m, b_lo, b_hi);
             for (int b = b_lo; b < b_hi; ++b, ++ns) {
-                tc::mbar_wait(&bar_stgfull, ns & 1);
+                const float *sdy = stg + (size_t)(ns & 1) * 2 * SDW_STG, *sd1 = sdy + SDW_STG;
+                tc::mbar_wait(&bar_stgfull[ns & 1], (ns >> 1) & 1);
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const int st = g % SDW_STAGES, use = g / SDW_STAGES;
                     if (use > 0) tc::mbar_wait(&bar_empty[st], (use - 1) & 1);
                     const uint32_t base = tc::smem_u32(ring + (size_t)st * SDW_STAGE);
-                    for (int item = pw; item < 64 + 4 * SDW_BROWS; item += SDW_PROD_WARPS) {
-                        float v = 0.f;
-                        uint32_t a;
-                        if (item < 64) {          // dy3 operand: copy sa = item / 32, half h, row r
-                            const int sa = item >> 5, h = (item >> 4) & 1, r = item & 15;
-                            const int uu = c * SDW_R + r - sa;
-                            if (uu >= 0 && uu < U) v = sdy[(h * 32 + lane) * U + uu];
-                            a = base + (uint32_t)(((sa * 2 + h) * SDW_R + r) * 128 + lane * 4);
-                        } else {                  // d1 operand: copy sb, half h, row r
-                            const int ib = item - 64;
-                            const int sb = ib / (2 * SDW_BROWS), rem = ib - sb * 2 * SDW_BROWS;
-                            const int h = rem / SDW_BROWS, r = rem - h * SDW_BROWS;
-                            const int t = c * SDW_R + r + 2 * sb - pad;
-                            if (t >= 0 && t < U) v = sd1[(h * 32 + lane) * U + t];
-                            a = base + (uint32_t)(2 * SDW_A * 4 + ((sb * 2 + h) * SDW_BROWS + r) * 128 + lane * 4);
+                    constexpr int NA = 2 * 2 * (SDW_R / 4), NB = 2 * 2 * (SDW_BROWS / 4);
+                    for (int item = pw; item < NA + NB; item += SDW_PROD_WARPS) {
+                        const float *src;
+                        int pos, rows, copy, h, rq;
+                        uint32_t a, lo_off;
+                        if (item < NA) {          // dy3 operand: A[(sa, o)][u'] = dy3[o][u' - sa]
+                            copy = item / (2 * (SDW_R / 4));
+                            const int rem = item - copy * 2 * (SDW_R / 4);
+                            h = rem / (SDW_R / 4); rq = rem - h * (SDW_R / 4);
+                            rows = SDW_R; src = sdy; lo_off = SDW_A * 4;
+                            pos = c * SDW_R + 4 * rq + lb - copy;
+                            a = base;
+                        } else {                  // d1 operand: B[(sb, g)][rho] = d1[g][rho + 2 sb - pad]
+                            const int ib = item - NA;
+                            copy = ib / (2 * (SDW_BROWS / 4));
+                            const int rem = ib - copy * 2 * (SDW_BROWS / 4);
+                            h = rem / (SDW_BROWS / 4); rq = rem - h * (SDW_BROWS / 4);
+                            rows = SDW_BROWS; src = sd1; lo_off = SDW_B * 4;
+                            pos = c * SDW_R + 4 * rq + lb + 2 * copy - pad;
+                            a = base + 2 * SDW_A * 4;
                         }
-                        float hi, lo;
-                        tc::split_tf32(v, hi, lo);
-                        sdw_sts(sdw_swz(a), hi);
-                        sdw_sts(sdw_swz(a + (item < 64 ? SDW_A : SDW_B) * 4), lo);
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (pos >= 0 && pos < U) {
+                            const float *p = src + (h * 32 + 4 * la) * U + pos;
+                            v = make_float4(p[0], p[U], p[2 * U], p[3 * U]);
+                        }
+                        float4 hi, lo;
+                        tc::split_tf32(v.x, hi.x, lo.x);
+                        tc::split_tf32(v.y, hi.y, lo.y);
+                        tc::split_tf32(v.z, hi.z, lo.z);
+                        tc::split_tf32(v.w, hi.w, lo.w);
+                        a += (uint32_t)(((copy * 2 + h) * rows + 4 * rq + lb) * 128 + la * 16);
+                        sdw_sts4(sdw_swz(a), hi);
+                        sdw_sts4(sdw_swz(a + lo_off), lo);
                     }
                     tc::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&bar_full[st]);
                 }
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bar_stgempty);     // this warp no longer reads the staged sample
+                if (lane == 0) tc::mbar_arrive(&bar_stgempty[ns & 1]);     // this warp no longer reads the staged sample
             }
         }
     } else if (warp == 5) {
@@ -367,11 +384,13 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
                 int m, b_lo, b_hi;
                 unit_range(u, m, b_lo, b_hi);
                 for (int b = b_lo; b < b_hi; ++b, ++ns) {
-                    if (ns > 0) tc::mbar_wait(&bar_stgempty, (ns - 1) & 1);
+                    const int sb = ns & 1;
+                    if (ns >= 2) tc::mbar_wait(&bar_stgempty[sb], ((ns >> 1) - 1) & 1);
                     const int64_t n = (int64_t)m * B + b;
-                    tc::mbar_expect_tx(&bar_stgfull, 2 * bytes);
-                    tc::tma_load_1d(stg, dy3 + n * 64 * U, bytes, &bar_stgfull);
-                    tc::tma_load_1d(stg + SDW_STG, d1 + n * 64 * U, bytes, &bar_stgfull);
+                    float *dst = stg + (size_t)sb * 2 * SDW_STG;
+                    tc::mbar_expect_tx(&bar_stgfull[sb], 2 * bytes);
+                    tc::tma_load_1d(dst, dy3 + n * 64 * U, bytes, &bar_stgfull[sb]);
+                    tc::tma_load_1d(dst + SDW_STG, d1 + n * 64 * U, bytes, &bar_stgfull[sb]);
                 }
             }
         }
