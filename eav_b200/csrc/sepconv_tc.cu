@@ -38,21 +38,36 @@ constexpr int SCT_WSTAGES = 3;
 constexpr int SCT_NITER = SCT_NBLOCKS / SCT_BPS;       // ring stages consumed per sample pair
 constexpr size_t SCT_SMEM = ((size_t)4 * SCT_ACT + (size_t)SCT_WSTAGES * SCT_BPS * SCT_BLOCK) * 4;   // 196608 B
 
-// out[m][blk = k*8 + c8][n/8][cc/4][n%8][cc%4]:  n < 64 -> hi(Wk[n][8 c8 + cc][k]),  n >= 64 -> lo
+// out[m][blk = k*8 + c8][n/8][cc/4][n%8][cc%4]:  n < 64 -> hi(Wk[n][8 c8 + cc][k]),  n >= 64 -> lo.
+// Block (c8, m) stages the 64 x 8 x 16 weights it needs in shared memory with coalesced reads, then writes its
+// 16 tap blocks with coalesced stores.
 template <int MODE>
-__global__ void sepconv_wt_pack_kernel(const float *__restrict__ params, int64_t pstride, int64_t oW3,
-                                       float *__restrict__ out) {
-    const int m = blockIdx.y, blk = blockIdx.x;
-    const int k = blk >> 3, c8 = blk & 7;
-    for (int idx = threadIdx.x; idx < SCT_BLOCK; idx += blockDim.x) {
-        const int n = idx >> 3, cc = idx & 7;
-        const int o = n & 63, c = c8 * 8 + cc;
-        const float *W3 = params + (int64_t)m * pstride + oW3;           // [F2][G][K2]
-        const float w = MODE == 0 ? W3[(o * SCT_C + c) * SCT_K + k] : W3[(c * SCT_C + o) * SCT_K + (SCT_K - 1 - k)];
-        float hi, lo;
-        tc::split_tf32(w, hi, lo);
-        out[((int64_t)m * SCT_NBLOCKS + blk) * SCT_BLOCK + (n >> 3) * 64 + (cc >> 2) * 32 + (n & 7) * 4 + (cc & 3)] =
-            n < 64 ? hi : lo;
+__global__ void __launch_bounds__(256) sepconv_wt_pack_kernel(const float *__restrict__ params, int64_t pstride,
+                                                              int64_t oW3, float *__restrict__ out) {
+    __shared__ float ws[64][8 * SCT_K + 1];          // [n][cc*16 + k]
+    const int m = blockIdx.y, c8 = blockIdx.x;
+    const float *W3 = params + (int64_t)m * pstride + oW3;           // [F2][G][K2]
+    for (int i = threadIdx.x; i < 64 * 8 * SCT_K; i += blockDim.x) {
+        // MODE 0: rows n = o, columns c = 8 c8 + cc: W3[n][8 c8 .. 8 c8 + 7][0..15] is 128 contiguous floats
+        // MODE 1: rows n = g, columns c = o:           W3[8 c8 + cc][n][0..15]
+        if (MODE == 0) {
+            const int n = i >> 7, r = i & 127;
+            ws[n][r] = W3[(n * SCT_C + c8 * 8) * SCT_K + r];
+        } else {
+            const int cc = i >> 10, r = i & 1023, n = r >> 4, k = r & 15;
+            ws[n][cc * SCT_K + (SCT_K - 1 - k)] = W3[((c8 * 8 + cc) * SCT_C) * SCT_K + r];
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < SCT_K; ++k) {
+        float *dst = out + ((int64_t)m * SCT_NBLOCKS + k * 8 + c8) * SCT_BLOCK;
+        for (int idx = threadIdx.x; idx < SCT_BLOCK; idx += blockDim.x) {
+            // idx = (n/8)*64 + (cc/4)*32 + (n%8)*4 + cc%4
+            const int n = (idx >> 6) * 8 + ((idx >> 2) & 7), cc = ((idx >> 5) & 1) * 4 + (idx & 3);
+            float hi, lo;
+            tc::split_tf32(ws[n & 63][cc * SCT_K + k], hi, lo);
+            dst[idx] = n < 64 ? hi : lo;
+        }
     }
 }
 
@@ -463,17 +478,29 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
     if (warp == 4) tc::tmem_dealloc(tmem, 512);
 }
 
-// grads[m][oW3 + (o*64 + g)*16 + k] = sum_s part[(m*S + s)][k][o][g]   (fixed order)
-__global__ void sepconv_dw_reduce_kernel(const float *__restrict__ part, int S, int64_t pstride, int64_t oW3,
-                                         float *__restrict__ grads) {
+// grads[m][oW3 + (o*64 + g)*16 + k] = sum_s part[(m*S + s)][k][o][g]   (fixed order).  Thread = (o, g): reads are
+// coalesced along g for every (s, k), the 16 taps leave as one contiguous 64-byte store.
+__global__ void __launch_bounds__(256) sepconv_dw_reduce_kernel(const float *__restrict__ part, int S, int64_t pstride,
+                                                                 int64_t oW3, float *__restrict__ grads) {
     const int m = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // (k, o, g), g fastest
-    if (i >= 16 * 4096) return;
-    const int g = i & 63, o = (i >> 6) & 63, k = i >> 12;
-    const float *p = part + (int64_t)m * S * 65536 + i;
-    float s = 0.f;
-    for (int j = 0; j < S; ++j) s += p[(int64_t)j * 65536];
-    grads[(int64_t)m * pstride + oW3 + (o * 64 + g) * 16 + k] = s;
+    const int og = blockIdx.x * blockDim.x + threadIdx.x;      // o * 64 + g
+    const float *p = part + (int64_t)m * S * 65536 + og;
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (int j = 0; j < S; ++j) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] += p[(int64_t)j * 65536 + k * 4096];
+    }
+    float4 *dst = reinterpret_cast<float4 *>(grads + (int64_t)m * pstride + oW3 + (int64_t)og * 16);
+    if (((pstride | oW3) & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
+        float *d = reinterpret_cast<float *>(dst);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = acc[k];
+    }
 }
 
 }  // namespace
@@ -492,8 +519,8 @@ int launch_sepconv_tc(const NetDims &d, int mode, const float *in, const float *
                       float *part, int *part_rows, cudaStream_t st) {
     EAV_REQUIRE(wt_scratch != nullptr, EAV_ERR_BAD_ARG, "sepconv_tc: no weight scratch");
     float *wt = wt_scratch + (mode ? (size_t)d.M * SCT_NBLOCKS * SCT_BLOCK : 0);
-    if (mode == 0) sepconv_wt_pack_kernel<0><<<dim3(SCT_NBLOCKS, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
-    else sepconv_wt_pack_kernel<1><<<dim3(SCT_NBLOCKS, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
+    if (mode == 0) sepconv_wt_pack_kernel<0><<<dim3(8, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
+    else sepconv_wt_pack_kernel<1><<<dim3(8, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
     EAV_CUDA_LAUNCH_CHECK("sepconv_wt_pack");
     static bool attr_set = false;
     if (!attr_set) {
@@ -548,7 +575,7 @@ int launch_sepconv_dw_tc(const NetDims &d, const float *dy3, const float *d1, fl
     sepconv_dw_tc_kernel<<<units < sms ? units : sms, SDW_THREADS, SDW_SMEM, st>>>(dy3, d1, part, d.M, d.B, d.T4,
                                                                                    d.pad2l, S);
     EAV_CUDA_LAUNCH_CHECK("sepconv_bwd_dw_tc");
-    sepconv_dw_reduce_kernel<<<dim3(65536 / 256, d.M), 256, 0, st>>>(part, S, d.pstride, d.oW3, grads);
+    sepconv_dw_reduce_kernel<<<dim3(4096 / 256, d.M), 256, 0, st>>>(part, S, d.pstride, d.oW3, grads);
     EAV_CUDA_LAUNCH_CHECK("sepconv_dw_reduce");
     return 0;
 }
