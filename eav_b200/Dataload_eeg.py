@@ -172,6 +172,37 @@ class DataLoadEEG:
         self.label_div = y
         return self.seg_f_div_device, y
 
+    # ------------------------------------------------------------------ legacy order (the paper's 5-class setting)
+    def prepare_data_legacy_device(self, band=(3, 50)):
+        """CNN_tensorflow/CNN_EEG_tf.py:64-75,180-206 on the GPU: band-pass the raw recording at fs_orig
+        (butter(5, band, 'band', fs=fs_orig), continuous over the trials), THEN resample_poly to fs_target, split
+        every trial into 4 epochs, keep classes {1,3,5,7,9} and remap them to 0..4 (rows [1,3,5,7,9] of the one-hot
+        label matrix, :206).  Returns (x [N][Chans][500] float32 on the device, y int64 (N,) in 0..4)."""
+        ch, t, tri = self.seg.shape
+        seg = self.seg if np.asarray(self.seg).dtype == np.float32 else np.asarray(self.seg, dtype=np.float32)
+        raw = self._raw_device(seg)
+        n_sub = 4
+        down = int(self.fs_orig / self.fs_target)
+        eng = PreprocEngine(1, n_trials=tri, n_chans=ch, trial_len=t, down=down, n_taps=2 * 10 * down + 1,
+                            n_sections=5, n_sub=n_sub, raw_dtype=torch.float32, device=self._dev(), order=1)
+        slot, y = epoch_slots(self.label, n_sub)
+        n_ep = int((slot >= 0).sum()) * n_sub
+        sos = butter(5, list(band), btype='band', fs=self.fs_orig, output='sos')       # CNN_EEG_tf.py:69
+        ep = eng.run(raw, decimation_taps(down), sos, torch.from_numpy(slot).unsqueeze(0).to(self._dev()), n_ep)
+        self.seg_f_div_device = ep[0]
+        self.label_div = (np.asarray(y) - 1) // 2
+        return self.seg_f_div_device, self.label_div
+
+    def prepare_data_legacy(self, band=(3, 50)):
+        """load_mat_data() + prepare_data_legacy_device(); returns numpy (x float32 (N, Chans, 500), y in 0..4),
+        which EAVDataSplit(x, y).get_split(h_idx=56) splits 280/120 as the paper does."""
+        self.load_mat_data()
+        if self.seg is None:
+            return self.seg_f_div, self.label_div
+        x_dev, y = self.prepare_data_legacy_device(band)
+        self.seg_f_div = x_dev.cpu().numpy()
+        return self.seg_f_div, self.label_div
+
     # legacy names documented in the reference README (README.md:186-199) and used at EEGNet_tor.py:149
     data_mat = load_mat_data
     bandpass = bandpass_filter

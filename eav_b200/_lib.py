@@ -20,7 +20,7 @@ EAV_DROPOUT_NONE, EAV_DROPOUT_MASK, EAV_DROPOUT_PHILOX = 0, 1, 2
 
 class PreprocCfg(Structure):
     _fields_ = [(n, c_int32) for n in ("n_subjects", "n_trials", "n_chans", "trial_len", "down", "n_taps",
-                                       "n_sections", "n_sub", "raw_is_f64", "reserved")]
+                                       "n_sections", "n_sub", "raw_is_f64", "order")]
 
 
 class EegnetCfg(Structure):

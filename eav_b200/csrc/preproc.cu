@@ -258,7 +258,10 @@ __global__ void __launch_bounds__(SOS_THREADS)
 sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, int n_chans, int n_trials,
            int chunk_len, int64_t n_dec, const int32_t *__restrict__ kept_trial, int n_kept,
            double *__restrict__ zstate, const double *__restrict__ start, int n_sub, int ep_len,
-           int n_epochs_out, float *__restrict__ epochs, int64_t n_work) {
+           int n_epochs_out, float *__restrict__ epochs, int64_t n_work, int raw_layout) {
+    // raw_layout = 1 (legacy order, band-pass BEFORE decimation): `dec` is the raw recording
+    // [S][trial][ch][chunk_len], every trial is filtered (kept_trial == nullptr: identity) and the output row
+    // goes to the same position of `epochs` (= the filtered recording, n_sub = 1, ep_len = chunk_len).
     __shared__ float tile[SOS_THREADS][SOS_TILE + 1];
     __shared__ int64_t row_src[SOS_THREADS];   // offset of the chunk in dec, or -1
     __shared__ int64_t row_dst[SOS_THREADS];   // offset of the trial's first epoch row in epochs
@@ -271,17 +274,23 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
         if (APPLY) {
             my_seq = w / n_kept;                       // (subject, channel)
             my_slot = (int)(w - my_seq * n_kept);
-            my_trial = kept_trial[(my_seq / n_chans) * n_kept + my_slot];
+            my_trial = kept_trial ? kept_trial[(my_seq / n_chans) * n_kept + my_slot] : my_slot;
         } else {
             my_seq = w / n_trials;
             my_trial = (int)(w - my_seq * n_trials);
         }
     }
     const bool my_ok = my_trial >= 0;
-    row_src[tid] = my_ok ? my_seq * n_dec + (int64_t)my_trial * chunk_len : -1;
-    if (APPLY) {
-        int64_t subj = my_seq / n_chans, ch = my_seq - subj * n_chans;
-        row_dst[tid] = ((subj * n_epochs_out + (int64_t)my_slot * n_sub) * n_chans + ch) * ep_len;
+    if (raw_layout) {
+        const int64_t subj = my_seq / n_chans, ch = my_seq - subj * n_chans;
+        row_src[tid] = my_ok ? ((subj * n_trials + my_trial) * n_chans + ch) * (int64_t)chunk_len : -1;
+        if (APPLY) row_dst[tid] = row_src[tid];
+    } else {
+        row_src[tid] = my_ok ? my_seq * n_dec + (int64_t)my_trial * chunk_len : -1;
+        if (APPLY) {
+            int64_t subj = my_seq / n_chans, ch = my_seq - subj * n_chans;
+            row_dst[tid] = ((subj * n_epochs_out + (int64_t)my_slot * n_sub) * n_chans + ch) * ep_len;
+        }
     }
 
     double s0[NSEC], s1[NSEC];
@@ -479,7 +488,7 @@ static PreSide *pre_side_stream() {
     return &pool[dev];
 }
 
-struct PreLayout { size_t dec, z, start, kept, gtab, total; };
+struct PreLayout { size_t dec, z, start, kept, gtab, filt, total; };
 static PreLayout pre_layout(const eav_preproc_cfg *c, bool own_dec) {
     PreLayout l;
     size_t o = 0;
@@ -491,6 +500,9 @@ static PreLayout pre_layout(const eav_preproc_cfg *c, bool own_dec) {
     l.start = take(seqs * c->n_trials * 2 * c->n_sections * sizeof(double));
     l.kept = take((size_t)c->n_subjects * c->n_trials * sizeof(int32_t));
     l.gtab = take((size_t)(c->trial_len / c->down) * 2 * c->n_sections * sizeof(double));
+    // legacy order: the band-passed recording at fs_orig (fp32, raw layout)
+    l.filt = take(c->order == EAV_PREPROC_ORDER_BANDPASS_FIRST
+                      ? (size_t)c->n_subjects * c->n_trials * c->n_chans * c->trial_len * sizeof(float) : 0);
     l.total = o;
     return l;
 }
@@ -506,6 +518,10 @@ static int check_cfg(const eav_preproc_cfg *c) {
     EAV_REQUIRE(c->trial_len % c->down == 0, EAV_ERR_UNSUPPORTED, "preproc: trial_len %% down != 0");
     EAV_REQUIRE((c->trial_len / c->down) % c->n_sub == 0, EAV_ERR_UNSUPPORTED, "preproc: trial not divisible into n_sub epochs");
     EAV_REQUIRE(c->n_chans <= 65535 && c->n_subjects <= 65535, EAV_ERR_UNSUPPORTED, "preproc: too many channels/subjects");
+    EAV_REQUIRE(c->order == EAV_PREPROC_ORDER_DECIMATE_FIRST || c->order == EAV_PREPROC_ORDER_BANDPASS_FIRST,
+                EAV_ERR_BAD_ARG, "preproc: unknown order %d", c->order);
+    EAV_REQUIRE(c->order == EAV_PREPROC_ORDER_DECIMATE_FIRST || !c->raw_is_f64, EAV_ERR_UNSUPPORTED,
+                "preproc: the band-pass-first order takes float32 recordings");
     return 0;
 }
 
@@ -528,7 +544,7 @@ static int run_sos(const eav_preproc_cfg *c, const float *dec, const SosCoef &co
                                                                                                 n_dec, z, work1);
     else
         sos_kernel<NSEC, false><<<(unsigned)cdiv64(work1, SOS_THREADS), SOS_THREADS, 0, st>>>(
-            dec, co, c->n_chans, c->n_trials, chunk, n_dec, nullptr, 0, z, nullptr, c->n_sub, chunk / c->n_sub, 0, nullptr, work1);
+            dec, co, c->n_chans, c->n_trials, chunk, n_dec, nullptr, 0, z, nullptr, c->n_sub, chunk / c->n_sub, 0, nullptr, work1, 0);
     EAV_CUDA_LAUNCH_CHECK("sos_state");
     sos_carry_kernel<NSEC><<<(unsigned)cdiv64(seqs, 64), 64, 0, st>>>(z, A, c->n_trials, seqs, start);
     EAV_CUDA_LAUNCH_CHECK("sos_carry");
@@ -536,10 +552,49 @@ static int run_sos(const eav_preproc_cfg *c, const float *dec, const SosCoef &co
     if (work3 > 0) {
         sos_kernel<NSEC, true><<<(unsigned)cdiv64(work3, SOS_THREADS), SOS_THREADS, 0, st>>>(
             dec, co, c->n_chans, c->n_trials, chunk, n_dec, kept, n_kept, nullptr, start, c->n_sub, chunk / c->n_sub,
-            n_epochs_out, epochs, work3);
+            n_epochs_out, epochs, work3, 0);
         EAV_CUDA_LAUNCH_CHECK("sos_apply");
     }
     return 0;
+}
+
+// Legacy order (CNN_tensorflow/CNN_EEG_tf.py:64-75,182-189): band-pass the RAW recording at fs_orig, continuous over
+// all trials of a (subject, channel) sequence, into `filt` (same layout as raw); the FIR then decimates `filt`.
+template <int NSEC>
+static int run_sos_raw(const eav_preproc_cfg *c, const float *raw, const SosCoef &co, const CarryMat &A, double *z,
+                       double *start, float *filt, cudaStream_t st) {
+    const int chunk = c->trial_len;
+    const int64_t seqs = (int64_t)c->n_subjects * c->n_chans;
+    const int64_t work = seqs * c->n_trials;
+    sos_kernel<NSEC, false><<<(unsigned)cdiv64(work, SOS_THREADS), SOS_THREADS, 0, st>>>(
+        raw, co, c->n_chans, c->n_trials, chunk, 0, nullptr, 0, z, nullptr, 1, chunk, 0, nullptr, work, 1);
+    EAV_CUDA_LAUNCH_CHECK("sos_state(raw)");
+    sos_carry_kernel<NSEC><<<(unsigned)cdiv64(seqs, 64), 64, 0, st>>>(z, A, c->n_trials, seqs, start);
+    EAV_CUDA_LAUNCH_CHECK("sos_carry");
+    sos_kernel<NSEC, true><<<(unsigned)cdiv64(work, SOS_THREADS), SOS_THREADS, 0, st>>>(
+        raw, co, c->n_chans, c->n_trials, chunk, 0, nullptr, c->n_trials, nullptr, start, 1, chunk, 0, filt, work, 1);
+    EAV_CUDA_LAUNCH_CHECK("sos_apply(raw)");
+    return 0;
+}
+
+// epochs[s][slot*n_sub + q][ch][off] = dec[s][ch][trial*chunk + q*ep_len + off] for the kept trials
+// (segment_and_select_classes / mysplit: CNN_EEG_tf.py:84-101,191-199)
+__global__ void epoch_gather_kernel(const float *__restrict__ dec, const int32_t *__restrict__ kept_trial, int n_kept,
+                                    int n_chans, int64_t n_dec, int chunk, int n_sub, int n_epochs_out,
+                                    float *__restrict__ epochs, int64_t total) {
+    const int ep_len = chunk / n_sub;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i % chunk);
+        int64_t r = i / chunk;
+        const int ch = (int)(r % n_chans); r /= n_chans;
+        const int slot = (int)(r % n_kept);
+        const int64_t subj = r / n_kept;
+        const int trial = kept_trial[subj * n_kept + slot];
+        if (trial < 0) continue;
+        const int q = t / ep_len, off = t - q * ep_len;
+        epochs[((subj * n_epochs_out + (int64_t)slot * n_sub + q) * n_chans + ch) * ep_len + off] =
+            dec[(subj * n_chans + ch) * n_dec + (int64_t)trial * chunk + t];
+    }
 }
 
 template <typename TIn, bool SKIP>
@@ -628,7 +683,9 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
         EAV_REQUIRE(r[3] == 1.0, EAV_ERR_UNSUPPORTED, "preproc_run: sos a0 must be 1 (scipy normalises it)");
         co.b0[k] = r[0]; co.b1[k] = r[1]; co.b2[k] = r[2]; co.a1[k] = r[4]; co.a2[k] = r[5];
     }
-    const int chunk = cfg->trial_len / cfg->down;
+    const bool bp_first = cfg->order == EAV_PREPROC_ORDER_BANDPASS_FIRST;
+    const int chunk = cfg->trial_len / cfg->down;               // decimated samples per trial
+    const int sos_chunk = bp_first ? cfg->trial_len : chunk;    // samples per trial at the rate the SOS runs at
     CarryMat A;
     memset(&A, 0, sizeof(A));
     {
@@ -647,7 +704,7 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
             for (int k = 0; k < NSEC; ++k) { Am[(2 * k) * NS + e] = s0[k]; Am[(2 * k + 1) * NS + e] = s1[k]; }
         }
         for (int i = 0; i < NS; ++i) P[i * NS + i] = 1.0L;
-        int pw = chunk;   // P = Am^chunk by binary exponentiation
+        int pw = sos_chunk;   // P = Am^chunk by binary exponentiation
         while (pw > 0) {
             if (pw & 1) {
                 for (int i = 0; i < NS; ++i) for (int j = 0; j < NS; ++j) {
@@ -711,6 +768,30 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
         const int Hh = (cfg->n_taps - 1) / 2;
         for (int t = 0; t < cfg->n_taps; ++t)
             if (t != Hh && ((t - Hh) % cfg->down) == 0 && fabs(taps[t]) > 1e-15 * fabs(taps[Hh])) skip_zero = false;
+    }
+    if (bp_first) {
+        // band-pass at fs_orig over the raw recording -> filt, decimate filt -> dec, gather the kept epochs
+        float *filt = reinterpret_cast<float *>(ws + l.filt);
+        const float *rawf = reinterpret_cast<const float *>(raw);
+        switch (NSEC) {
+            case 1: rc = run_sos_raw<1>(cfg, rawf, co, A, z, start, filt, st); break;
+            case 2: rc = run_sos_raw<2>(cfg, rawf, co, A, z, start, filt, st); break;
+            case 3: rc = run_sos_raw<3>(cfg, rawf, co, A, z, start, filt, st); break;
+            case 4: rc = run_sos_raw<4>(cfg, rawf, co, A, z, start, filt, st); break;
+            case 5: rc = run_sos_raw<5>(cfg, rawf, co, A, z, start, filt, st); break;
+            default: rc = run_sos_raw<6>(cfg, rawf, co, A, z, start, filt, st); break;
+        }
+        if (rc) return rc;
+        rc = run_fir<float>(cfg, filt, ft, skip_zero, dec, st);
+        if (rc) return rc;
+        if (n_kept > 0) {
+            const int64_t n_dec = (int64_t)cfg->n_trials * chunk;
+            const int64_t tot = (int64_t)cfg->n_subjects * n_kept * cfg->n_chans * chunk;
+            epoch_gather_kernel<<<(unsigned)std::min<int64_t>(cdiv64(tot, 256), 148 * 32), 256, 0, st>>>(
+                dec, kept, n_kept, cfg->n_chans, n_dec, chunk, cfg->n_sub, n_epochs_out, epochs, tot);
+            EAV_CUDA_LAUNCH_CHECK("epoch_gather");
+        }
+        return 0;
     }
     // Optional grouping (EAV_PREPROC_GROUPS=n): the FIR of group i+1 on the caller's stream, the SOS
     // passes of group i on a forked stream.  The idea was to overlap the fp32/HBM-bound FIR with the

@@ -242,7 +242,9 @@ class PreprocEngine:
     """Decimate + band-pass + epoch a batch of subjects on the GPU (Dataload_eeg.py:85-152)."""
 
     def __init__(self, n_subjects, n_trials=200, n_chans=30, trial_len=10000, down=5, n_taps=101, n_sections=5,
-                 n_sub=4, raw_dtype=torch.float32, device=None):
+                 n_sub=4, raw_dtype=torch.float32, device=None, order=0):
+        """order 0: decimate then band-pass at fs_target (Dataload_eeg.py); 1: band-pass at fs_orig then decimate
+        (legacy CNN_EEG_tf.py:64-75,182-189; `sos` must then be designed for fs_orig)."""
         _lib.require_device()
         self.lib = _lib.load()
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -250,6 +252,7 @@ class PreprocEngine:
         c.n_subjects, c.n_trials, c.n_chans, c.trial_len = n_subjects, n_trials, n_chans, trial_len
         c.down, c.n_taps, c.n_sections, c.n_sub = down, n_taps, n_sections, n_sub
         c.raw_is_f64 = int(raw_dtype == torch.float64)
+        c.order = int(order)
         self.cfg = c
         self.raw_dtype = raw_dtype
         nbytes = self.lib.eav_preproc_workspace_bytes(ctypes.byref(c))

@@ -59,8 +59,14 @@ typedef struct eav_preproc_cfg {
     int32_t n_sections;    /* biquads in the SOS cascade (5)                     */
     int32_t n_sub;         /* epochs per trial (4)                               */
     int32_t raw_is_f64;    /* 0: raw is float32, 1: raw is float64               */
-    int32_t reserved;
+    int32_t order;         /* EAV_PREPROC_ORDER_*                                */
 } eav_preproc_cfg;
+
+/* Dataload_eeg.py:85-121: resample_poly to fs_target, then band-pass at fs_target (the shipped order). */
+#define EAV_PREPROC_ORDER_DECIMATE_FIRST 0
+/* CNN_tensorflow/CNN_EEG_tf.py:64-75,182-189 (legacy): band-pass the raw recording at fs_orig (`sos` designed
+ * for fs_orig), then resample_poly.  float32 recordings only; needs one more raw-sized buffer in the workspace. */
+#define EAV_PREPROC_ORDER_BANDPASS_FIRST 1
 
 size_t eav_preproc_workspace_bytes(const eav_preproc_cfg *cfg);
 

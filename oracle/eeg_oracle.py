@@ -205,6 +205,27 @@ def prepare_data(raw: np.ndarray, label: np.ndarray, band, fs_orig=500, fs_targe
     return epoch_gather(filt, label, trial_len, 4)
 
 
+def prepare_data_legacy(raw: np.ndarray, label: np.ndarray, band=(3, 50), fs_orig=500, fs_target=100):
+    """The legacy pipeline of CNN_tensorflow/CNN_EEG_tf.py (the paper's 5-class 280/120 setting), minus .mat I/O:
+      :64-75   Bandpass: butter(5, band, 'band', fs=fs_orig) + sosfilt on the continuous 500 Hz sequence of each
+               channel (trials concatenated in time), i.e. the band-pass runs BEFORE the decimation;
+      :182-189 resample_poly(up=1, down=fs_orig/fs_target) of that sequence;
+      :84-101  mysplit: trial k -> epochs 4k..4k+3 (500 samples each), labels repeated 4x;
+      :191-206 keep the trials of classes {1,3,5,7,9}; label_5class = rows [1,3,5,7,9] of the one-hot matrix,
+               i.e. class index (c - 1) / 2 in 0..4.
+    raw: [trials][ch][time].  Returns (x [n_epochs][ch][500] f64, y int64 in 0..4, onehot (5, n_epochs))."""
+    down = int(fs_orig / fs_target)
+    raw = np.asarray(raw)
+    n_tr, n_ch, tl = raw.shape
+    seqs = np.ascontiguousarray(np.transpose(raw, (1, 0, 2)).reshape(n_ch, n_tr * tl), dtype=np.float64)
+    filt = sosfilt(butter_sos(band, fs_orig), seqs)                       # [ch][trials*tl] at fs_orig
+    dec = fir_decimate(filt.reshape(n_ch, n_tr, tl).transpose(1, 0, 2), decimation_taps(down), down)
+    x, y = epoch_gather(dec, label, tl // down, 4)
+    y5 = (y - 1) // 2
+    onehot = (np.arange(5)[:, None] == y5[None, :]).astype(np.float64)
+    return x, y5, onehot
+
+
 # ----------------------------------------------------------------------------
 # S1-S3  split  (EAV_datasplit.py:12-40)
 # ----------------------------------------------------------------------------

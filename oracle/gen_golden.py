@@ -249,10 +249,59 @@ def gen_cnn_eeg(ns):
         save(f"cnn_eeg_{tag}.npz", **out)
 
 
+def ref_legacy_functions():
+    """`Bandpass` and `mysplit` of CNN_tensorflow/CNN_EEG_tf.py, compiled from the reference file's own source.
+    The module cannot be imported (it needs TensorFlow and runs its training script at import time), so only these
+    two FunctionDef nodes are executed, unmodified, with numpy/scipy in their globals."""
+    import ast
+    path = "/root/reference/CNN_tensorflow/CNN_EEG_tf.py"
+    src = open(path).read()
+    tree = ast.parse(src)
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("Bandpass", "mysplit")]
+    assert len(wanted) == 2
+    from scipy import signal
+    from scipy.signal import butter
+    g = {"np": np, "signal": signal, "butter": butter}
+    exec(compile(ast.Module(body=wanted, type_ignores=[]), path, "exec"), g)
+    return g["Bandpass"], g["mysplit"]
+
+
+def gen_legacy():
+    """Legacy order (band-pass at 500 Hz, then decimate) on dataset-shaped subject 1: the reference's own
+    Bandpass()/mysplit() plus the module-level glue of CNN_EEG_tf.py:180-206, which is restated line by line."""
+    from scipy import signal
+    Bandpass, mysplit = ref_legacy_functions()
+    raw, label = O.synth_subject(1)
+    cnt_ = np.transpose(raw.astype(np.float64), (2, 1, 0))               # (10000, 30, 200) as loadmat returns it
+    Label = label
+    cnt_f = Bandpass(cnt_, freq=[3, 50], fs=500)                            # :180
+    tm = np.transpose(cnt_f, [0, 2, 1]).reshape([10000 * 200, 30], order='F')      # :185
+    tm2 = signal.resample_poly(tm, up=1, down=int(500 / 100), axis=0)      # :188
+    cnt_f2 = np.reshape(tm2, [2000, 200, 30], order='F')                   # :189
+    cnt_seg = np.transpose(cnt_f2, [1, 0, 2])                               # :191
+    cnt_seg_split, Label_split = mysplit(cnt_seg, Label)                    # :194
+    dat = np.transpose(cnt_seg_split, (0, 2, 1)).reshape((800, 30, 500, 1))  # :196
+    selected_classes = [1, 3, 5, 7, 9]
+    selected_indices = np.isin(np.argmax(Label_split, axis=0), selected_classes)   # :201
+    data_5class = dat[selected_indices]                                     # :203
+    aa = Label_split[:, selected_indices]
+    label_5class = aa[selected_classes, :]                                  # :206
+    x = data_5class[..., 0]                                                 # (400, 30, 500)
+    save("preproc_legacy_subject1_digest.npz",
+         label=label.astype(np.uint8), onehot=label_5class.astype(np.uint8),
+         x_sub=x[::25, ::7, ::20].copy(), x_epoch_sum=x.sum(axis=(1, 2)),
+         x_chan_rms=np.sqrt((x ** 2).mean(axis=(0, 2))),
+         filt500_sub=cnt_f[::500, ::7, ::25].copy())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    ns = ref_shim.load()
     torch.set_num_threads(8)
+    if "--only-legacy" in sys.argv:
+        gen_legacy()
+        sys.exit(0)
+    ns = ref_shim.load()
     gen_preproc(ns)
+    gen_legacy()
     gen_eegnet_tor(ns)
     gen_cnn_eeg(ns)

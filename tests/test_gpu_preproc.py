@@ -97,6 +97,59 @@ def test_dataset_shaped_subjects_vs_oracle_and_reference_digest(golden, subject_
         assert _chan_rel_err(ep[s], xo) < TOL, s
 
 
+def test_legacy_order_small_vs_oracle():
+    """order=1: band-pass at fs_orig over the raw recording, then decimate (CNN_EEG_tf.py:64-75,182-189)."""
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    rng = np.random.default_rng(11)
+    n_tr, n_ch, tl = 7, 3, 2000
+    raw = rng.standard_normal((n_tr, n_ch, tl)).astype(np.float32)
+    raw += (2.0 * np.sin(2 * np.pi * 0.3 * np.arange(n_tr * tl) / 500.0)).reshape(n_tr, 1, tl).astype(np.float32)
+    keep = np.array([1, 0, 1, 1, 0, 0, 1], dtype=bool)
+    label = np.zeros((10, n_tr)); label[np.where(keep, 1, 0), np.arange(n_tr)] = 1     # class 1 kept, class 0 dropped
+    eng = PreprocEngine(1, n_trials=n_tr, n_chans=n_ch, trial_len=tl, order=1)
+    sos = O.butter_sos((3, 50), 500.0)
+    ep, dec = eng.run(torch.from_numpy(raw[None]).cuda(), O.decimation_taps(5), sos,
+                      torch.from_numpy(_slots(keep)[None]).cuda(), 4 * int(keep.sum()), want_dec=True)
+    seqs = np.transpose(raw, (1, 0, 2)).reshape(n_ch, n_tr * tl).astype(np.float64)
+    filt = O.sosfilt(sos, seqs)
+    dec_o = O.fir_decimate(filt.reshape(n_ch, n_tr, tl).transpose(1, 0, 2), O.decimation_taps(5), 5)
+    rms = np.sqrt((dec_o ** 2).mean(axis=1))
+    assert (np.abs(dec.cpu().numpy()[0] - dec_o).max(axis=1) / rms).max() < TOL
+    xo, _ = O.epoch_gather(dec_o, label, tl // 5, 4)
+    assert _chan_rel_err(ep.cpu().numpy()[0], xo) < TOL
+
+
+def test_legacy_order_dataset_shaped_vs_reference_digest(golden, subject_pair):
+    """Subject 1 through the drop-in's prepare_data_legacy_device() against the output of the reference's own
+    Bandpass()/mysplit() (tests/golden/preproc_legacy_subject1_digest.npz) and against the oracle."""
+    import eeg_oracle as O
+    from eav_b200.Dataload_eeg import DataLoadEEG
+    raws, labels = subject_pair
+    g = golden("preproc_legacy_subject1_digest.npz")
+    D = DataLoadEEG(subject=1)
+    D.set_raw(np.transpose(raws[0], (2, 1, 0)), labels[0])       # (time, ch, trials) as loadmat returns it
+    x_dev, y = D.prepare_data_legacy_device(band=(3, 50))
+    x = x_dev.cpu().numpy()
+    assert x.shape == (400, 30, 500)
+    assert np.array_equal(np.eye(5, dtype=np.uint8)[y].T, g["onehot"])        # labels bit-exact, classes 0..4
+    rms = g["x_chan_rms"]
+    assert (np.abs(x[::25, ::7, ::20] - g["x_sub"]).max(axis=(0, 2)) / rms[::7]).max() < TOL
+    assert np.abs(x.astype(np.float64).sum(axis=(1, 2)) - g["x_epoch_sum"]).max() < 1e-2
+    xo, yo, _ = O.prepare_data_legacy(raws[0], labels[0], (3, 50))
+    assert np.array_equal(y, yo) and _chan_rel_err(x, xo) < TOL
+    # the paper's split: 56 train / 24 test epochs per class
+    from eav_b200.EAV_datasplit import EAVDataSplit
+    tr_x, tr_y, te_x, te_y = EAVDataSplit(x, y).get_split(h_idx=56)
+    assert tr_x.shape == (280, 30, 500) and te_x.shape == (120, 30, 500)
+
+
+def test_legacy_order_rejects_float64():
+    from eav_b200.ops import PreprocEngine
+    with pytest.raises(RuntimeError):
+        PreprocEngine(1, n_trials=2, n_chans=2, trial_len=100, raw_dtype=torch.float64, order=1)
+
+
 def test_properties_at_full_size(subject_pair):
     """Size-independent properties at the dataset shape: exact homogeneity under power-of-two
     scaling, and independence of a kept epoch from WHICH other trials are kept (the filter is

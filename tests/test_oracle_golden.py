@@ -78,6 +78,20 @@ def test_preproc_subject1_digest_vs_reference(golden):
     assert np.abs(x.sum(axis=(1, 2)) - g["x_epoch_sum"]).max() < 1e-8
 
 
+def test_legacy_order_digest_vs_reference(golden):
+    """Band-pass at 500 Hz BEFORE the decimation (CNN_EEG_tf.py:64-75,180-206): the fixture was produced by the
+    reference's own Bandpass()/mysplit() (oracle/gen_golden.py:gen_legacy)."""
+    g = golden("preproc_legacy_subject1_digest.npz")
+    raw, label = O.synth_subject(1)
+    assert np.array_equal(label.astype(np.uint8), g["label"])
+    x, y5, onehot = O.prepare_data_legacy(raw, label, (3, 50))
+    assert x.shape == (400, 30, 500) and set(np.unique(y5)) == {0, 1, 2, 3, 4}
+    assert np.array_equal(onehot.astype(np.uint8), g["onehot"])               # 5-class one-hot, 80 epochs per class
+    assert np.abs(x[::25, ::7, ::20] - g["x_sub"]).max() < 1e-11
+    assert np.abs(x.sum(axis=(1, 2)) - g["x_epoch_sum"]).max() < 1e-8
+    assert np.abs(np.sqrt((x ** 2).mean(axis=(0, 2))) - g["x_chan_rms"]).max() < 1e-11
+
+
 def test_epoch_plan_vs_reference(golden):
     g = golden("segment_plan.npz")
     keep, y, src_trial, src_sub = O.epoch_plan(g["label"].astype(np.float64))
