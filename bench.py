@@ -305,6 +305,30 @@ def main():
                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                             "traffic": None, "peak_source": peak_src,
                             "algorithmic_bytes": PREPROC_BYTES_PER_SUBJECT * M}}
+        # the legacy order (band-pass at 500 Hz over the raw recording, then decimate: CNN_EEG_tf.py:64-75,180-189) on
+        # a bounded number of subjects (it needs one more raw-sized buffer); reported beside the shipped order
+        try:
+            from scipy.signal import butter as _butter
+            ML = min(M, 8)
+            eng2 = ops.PreprocEngine(ML, device=dev, order=1)
+            sos500 = _butter(5, [3, 50], btype="band", fs=500, output="sos")
+            ep2 = torch.empty(ML, 400, 30, 500, dtype=torch.float32, device=dev)
+            eng2.run(raw[:ML], taps, sos500, slot[:ML].contiguous(), 400, epochs=ep2)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                eng2.run(raw[:ML], taps, sos500, slot[:ML].contiguous(), 400, epochs=ep2)
+            e1.record()
+            torch.cuda.synchronize()
+            lms = e0.elapsed_time(e1) / reps
+            # raw read twice (state pass, apply pass) + filtered written and read + decimated written and read + epochs
+            lbytes = ML * (4 * 240e6 + 2 * 48e6 + 24e6)
+            pre["bandpass_first_order"] = {"ms": lms, "subjects": ML, "ms_per_subject": lms / ML,
+                                           "algorithmic_bytes": lbytes, "achieved_gbs": lbytes / (lms * 1e-3) / 1e9,
+                                           "frac_of_hbm_peak": lbytes / (lms * 1e-3) / 1e9 / hbm_peak}
+            del eng2, ep2
+        except Exception as e:  # noqa: BLE001
+            pre["bandpass_first_order"] = {"error": repr(e)}
         # labels {1,3,5,7,9} -> 0..4 (harness remap) and the reference's 280/120 split
         tr_rows, tr_y = [], []
         for s in range(M):

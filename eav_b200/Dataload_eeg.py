@@ -71,10 +71,13 @@ class DataLoadEEG:
         if not os.path.exists(eeg_file_path):
             print(f'[Error] EEG data not found for {subject_str}')
             return
-        mat = scipy.io.loadmat(eeg_file_path)
-        cnt_ = np.array(mat.get('seg1')) if 'seg1' in mat else np.array(mat.get('seg'))
-        mat_y = scipy.io.loadmat(label_file_path)
-        self.set_raw(cnt_, np.array(mat_y.get('label')))
+        # MAT v5 payload mapped in place when it is stored uncompressed (mat_ingest.read_mat_array); scipy.io.loadmat
+        # is the fallback for anything else.  `raw` is [trial][ch][time] = the file's own memory order.
+        from .mat_ingest import load_subject_mat
+        raw, label, _ = load_subject_mat(self.parent_directory, self.subject)
+        self.label = label
+        self.seg = np.transpose(raw, (1, 2, 0))                      # (Channels, Time, Trials) view, no copy
+        self._raw_trial_major = raw
         print(f'[Info] Loaded EEG data for {subject_str}')
 
     def set_raw(self, cnt, label):
@@ -93,7 +96,10 @@ class DataLoadEEG:
 
     def _raw_device(self, seg):
         """(Channels, Time, Trials) host array -> device tensor [1][trials][ch][time] (the .mat memory order)."""
-        arr = np.ascontiguousarray(np.transpose(np.asarray(seg), (2, 0, 1)))
+        if seg is self.seg and self._raw_trial_major is not None:
+            arr = np.ascontiguousarray(self._raw_trial_major)          # already in the kernels' layout
+        else:
+            arr = np.ascontiguousarray(np.transpose(np.asarray(seg), (2, 0, 1)))
         if arr.dtype not in (np.float32, np.float64):
             arr = arr.astype(np.float64)
         return torch.from_numpy(arr).unsqueeze(0).to(self._dev())
@@ -118,6 +124,7 @@ class DataLoadEEG:
         ident = np.tile(np.array([1.0, 0, 0, 1, 0, 0]), (5, 1))
         _, dec = eng.run(raw, decimation_taps(down), ident, slot, 0, want_dec=True)
         new_time = int(t * (self.fs_target / self.fs_orig))
+        self._raw_trial_major = None                                        # self.seg stops being the raw recording
         self._dec_device = dec                                              # [1][ch][tri*new_time]
         self.seg = dec[0].reshape(ch, tri, new_time).permute(0, 2, 1).cpu().numpy()   # (ch, new_time, tri)
 

@@ -187,3 +187,29 @@ def test_trainer_uni_validate_matches_oracle(golden):
             tot += float(EO.loss_fn(o, yb)); correct += int((o.argmax(1) == yb).sum()); nb += 1
     assert abs(loss - tot / nb) < 1e-4 * (tot / nb) and acc == correct / 16
     assert f"Validation - Loss: {tot / nb:.4f}, Accuracy: {correct / 16:.4f}" in out.getvalue()
+
+
+def test_mat_ingest_pipeline_matches_direct_path(tmp_path):
+    """prepare_subjects (zero-copy MAT reader + prefetch thread + copy stream) gives the epochs the
+    per-subject DataLoadEEG.prepare_data() gives, for both preprocessing orders, with slots being reused."""
+    import scipy.io
+    import eeg_oracle as O
+    from eav_b200 import mat_ingest as MI
+    from eav_b200.Dataload_eeg import DataLoadEEG
+    subs = [1, 2, 3, 4]
+    for s in subs:
+        folder = tmp_path / f"subject{s:02d}" / "EEG"
+        folder.mkdir(parents=True)
+        raw, label = O.synth_subject(s, n_trials=20, trial_len=10000)
+        scipy.io.savemat(str(folder / f"subject{s:02d}_eeg.mat"), {"seg": np.transpose(raw, (2, 1, 0))},
+                         do_compression=(s % 2 == 0))
+        scipy.io.savemat(str(folder / f"subject{s:02d}_eeg_label.mat"), {"label": label})
+    for legacy in (False, True):
+        got = {s: (x.clone(), y) for s, x, y in MI.prepare_subjects(str(tmp_path), subs, band=[3, 45], legacy_order=legacy)}
+        torch.cuda.synchronize()
+        for s in subs:
+            D = DataLoadEEG(subject=s, band=[3, 45], parent_directory=str(tmp_path))
+            D.load_mat_data()
+            x, y = D.prepare_data_legacy_device(band=(3, 45)) if legacy else D.prepare_data_device()
+            assert np.array_equal(got[s][1], y)
+            assert torch.equal(got[s][0], x), (legacy, s)
