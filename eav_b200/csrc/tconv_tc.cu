@@ -378,7 +378,7 @@ namespace {
 // One ring stage per producer warp: a warp then waits on every phase of its own stage's `empty` barrier in
 // order.  (With more warps than stages a warp could test a parity two phases ahead, which mbarrier parity
 // waits cannot distinguish from "already complete".)
-constexpr int TCW_PROD_WARPS = 6;
+constexpr int TCW_PROD_WARPS = 7;
 constexpr int TCW_THREADS = (5 + TCW_PROD_WARPS) * 32;
 constexpr int TCW_STAGES = TCW_PROD_WARPS;
 constexpr int TCW_XS = 896;                       // floats per x buffer (>= 32*15 + 384), 3584 B
