@@ -55,6 +55,48 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
+    auto finish_row = [&](int o, const float4 st, float s1, float s2) {
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0) {
+            part[((int64_t)n * F2 + o) * 2] = s1;
+            part[((int64_t)n * F2 + o) * 2 + 1] = s2;
+        }
+    };
+    if (T4 <= 128) {
+        // four rows per pass: 16 independent loads in flight per lane before the first dependent use
+        for (int o0 = warp * 4; o0 < F2; o0 += (blockDim.x >> 5) * 4) {
+            float yv[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float *src = y3 + ((int64_t)n * F2 + min(o0 + r, F2 - 1)) * T4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) yv[r][q] = (lane + 32 * q < T4) ? src[lane + 32 * q] : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int o = o0 + r;
+                if (o >= F2) break;
+                const float4 st = bn3[(int64_t)m * F2 + o];
+                float *dst = dz3 + ((int64_t)n * F2 + o) * T4;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int u = lane + 32 * q;
+                    if (u < T4) {
+                        const int v = u / P2;
+                        const float y = yv[r][q];
+                        const float g = (v < T32) ? dfeat_s[o * T32 + v] * elu_grad_from_pre(fmaf(y, st.z, st.w)) : 0.f;
+                        dst[u] = g;
+                        s1 += g;
+                        s2 = fmaf(g, (y - st.x) * st.y, s2);
+                    }
+                }
+                finish_row(o, st, s1, s2);
+            }
+        }
+        return;
+    }
     for (int o = warp; o < F2; o += blockDim.x >> 5) {
         const float4 st = bn3[(int64_t)m * F2 + o];
         const float *src = y3 + ((int64_t)n * F2 + o) * T4;
@@ -68,12 +110,7 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
             s1 += g;
             s2 = fmaf(g, (y - st.x) * st.y, s2);
         }
-        s1 = warp_sum(s1);
-        s2 = warp_sum(s2);
-        if (lane == 0) {
-            part[((int64_t)n * F2 + o) * 2] = s1;
-            part[((int64_t)n * F2 + o) * 2 + 1] = s2;
-        }
+        finish_row(o, st, s1, s2);
     }
 }
 
@@ -266,29 +303,32 @@ sepconv_bwd_dw_kernel(const float *__restrict__ dy3, const float *__restrict__ d
 // In place: dz (gradient w.r.t. the BatchNorm OUTPUT) -> gradient w.r.t. the BatchNorm INPUT,
 //   dy = k * (dz - c1 - xhat * c2)   (c1 = c2 = 0 in eval mode).  Tiny (43 MB at 1344 samples); it lets
 // the two block-2 conv gradient kernels stage their operand with plain asynchronous copies.
-__global__ void bn_bwd_apply_kernel(float *__restrict__ dz, const float *__restrict__ y,
-                                    const float4 *__restrict__ bnf, const float4 *__restrict__ bnb, int bn_train,
-                                    int B, int ch, int L, int64_t total) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t nc = i / L;
-        const int c = (int)(nc % ch), n = (int)(nc / ch);
-        const float4 kb = bnb[(int64_t)(n / B) * ch + c];
-        float v = dz[i];
-        if (bn_train) {
-            const float4 kf = bnf[(int64_t)(n / B) * ch + c];
-            v = kb.x * (v - kb.y - (y[i] - kf.x) * kf.y * kb.z);
-        } else {
-            v = kb.x * v;
-        }
-        dz[i] = v;
+// One warp per (sample, channel) row: the BN constants are loaded once per row, no per-element index division.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float *__restrict__ dz, const float *__restrict__ y,
+                                                           const float4 *__restrict__ bnf,
+                                                           const float4 *__restrict__ bnb, int bn_train, int B, int ch,
+                                                           int L, int64_t rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int c = (int)(row % ch);
+    const int64_t n = row / ch;
+    const float4 kb = bnb[(n / B) * ch + c];
+    const float4 kf = bnf[(n / B) * ch + c];
+    float *d = dz + row * L;
+    const float *yr = y + row * L;
+    const float a = kb.x, b = kb.x * kf.y * kb.z;          // dy = a (dz - c1) - b (y - mean)
+#pragma unroll 4
+    for (int u = lane; u < L; u += 32) {
+        const float v = d[u];
+        d[u] = bn_train ? fmaf(-b, yr[u] - kf.x, a * (v - kb.y)) : a * v;
     }
 }
 
 int launch_bn_bwd_apply(const NetDims &d, float *dz3, const float *y3, const float4 *bnf3, const float4 *bnb3,
                         cudaStream_t st) {
-    const int64_t total = (int64_t)d.N * d.F2 * d.T4;
-    int blocks = (int)std::min<int64_t>(cdiv64(total, 256), 148 * 16);
-    bn_bwd_apply_kernel<<<blocks, 256, 0, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, d.B, d.F2, d.T4, total);
+    const int64_t rows = (int64_t)d.N * d.F2;
+    bn_bwd_apply_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, d.B, d.F2, d.T4, rows);
     EAV_CUDA_LAUNCH_CHECK("bn_bwd_apply");
     return 0;
 }
