@@ -509,20 +509,42 @@ pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, co
         return keep ? dd1[e] * sc : 0.f;
     };
     if (P1 == 4 && (T & 3) == 0) {              // one pooling window == one aligned float4
-        for (int u = lane; 4 * u < T; u += 32) {
-            const float up = upstream(u);
-            const float4 y = *reinterpret_cast<const float4 *>(y2 + row * T + 4 * u);
-            float4 o;
-            o.x = up * elu_grad_from_pre(fmaf(y.x, st.z, st.w));
-            o.y = up * elu_grad_from_pre(fmaf(y.y, st.z, st.w));
-            o.z = up * elu_grad_from_pre(fmaf(y.z, st.z, st.w));
-            o.w = up * elu_grad_from_pre(fmaf(y.w, st.z, st.w));
-            *reinterpret_cast<float4 *>(dz2 + row * T + 4 * u) = o;
-            s1 += (o.x + o.y) + (o.z + o.w);
-            s2 = fmaf(o.x, (y.x - st.x) * st.y, s2);
-            s2 = fmaf(o.y, (y.y - st.x) * st.y, s2);
-            s2 = fmaf(o.z, (y.z - st.x) * st.y, s2);
-            s2 = fmaf(o.w, (y.w - st.x) * st.y, s2);
+        // lane = block of four consecutive pooled elements = one Philox counter (see pool1_fwd_kernel)
+        const int64_t e0 = row * T4, eb0 = e0 & ~(int64_t)3;
+        const int nblk = (int)((e0 - eb0 + T4 + 3) >> 2);
+        for (int blk = lane; blk < nblk; blk += 32) {
+            const int64_t eb = eb0 + 4 * (int64_t)blk;
+            float4 yv[4];
+            float up[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t u = eb + j - e0;
+                const bool ok = u >= 0 && u < T4;
+                yv[j] = ok ? *reinterpret_cast<const float4 *>(y2 + row * T + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+                up[j] = ok ? dd1[eb + j] * sc : 0.f;
+            }
+            uint32_t keep = 0xFu;
+            if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep4(seed, step, 1u, (uint64_t)(eb >> 2), p_drop);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t u = eb + j - e0;
+                if (u < 0 || u >= T4) continue;
+                bool kp = ((keep >> j) & 1u) != 0;
+                if (dropout_mode == EAV_DROPOUT_MASK) kp = mask1[eb + j] != 0;
+                const float upj = kp ? up[j] : 0.f;
+                const float4 y = yv[j];
+                float4 o;
+                o.x = upj * elu_grad_from_pre(fmaf(y.x, st.z, st.w));
+                o.y = upj * elu_grad_from_pre(fmaf(y.y, st.z, st.w));
+                o.z = upj * elu_grad_from_pre(fmaf(y.z, st.z, st.w));
+                o.w = upj * elu_grad_from_pre(fmaf(y.w, st.z, st.w));
+                *reinterpret_cast<float4 *>(dz2 + row * T + 4 * u) = o;
+                s1 += (o.x + o.y) + (o.z + o.w);
+                s2 = fmaf(o.x, (y.x - st.x) * st.y, s2);
+                s2 = fmaf(o.y, (y.y - st.x) * st.y, s2);
+                s2 = fmaf(o.z, (y.z - st.x) * st.y, s2);
+                s2 = fmaf(o.w, (y.w - st.x) * st.y, s2);
+            }
         }
     } else {
         for (int t = lane; t < T; t += 32) {

@@ -471,15 +471,45 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
     const float *src = y2 + row * (int64_t)T;
     const bool vec = P1 == 4 && (T & 3) == 0;      // one aligned 128-bit load per pooling window
     const float invp = 1.f / (float)P1;
+    if (vec) {
+        // Lane = one block of four consecutive output elements e = 4*blk .. 4*blk+3 (global element index, so the
+        // block is exactly one Philox counter): four independent 128-bit loads in flight and one Philox call per
+        // four dropout decisions.
+        const int64_t e0 = row * T4, eb0 = e0 & ~(int64_t)3;
+        const int nblk = (int)((e0 - eb0 + T4 + 3) >> 2);
+        for (int blk = lane; blk < nblk; blk += 32) {
+            const int64_t eb = eb0 + 4 * (int64_t)blk;
+            float4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t u = eb + j - e0;
+                v[j] = (u >= 0 && u < T4) ? *reinterpret_cast<const float4 *>(src + 4 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t keep = 0xFu;
+            if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep4(seed, step, 1u, (uint64_t)(eb >> 2), p_drop);
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t u = eb + j - e0;
+                float sj = (elu_f(fmaf(v[j].x, st.z, st.w)) + elu_f(fmaf(v[j].y, st.z, st.w)) +
+                            elu_f(fmaf(v[j].z, st.z, st.w)) + elu_f(fmaf(v[j].w, st.z, st.w))) * invp;
+                if (dropout_mode == EAV_DROPOUT_MASK) sj = (u >= 0 && u < T4 && mask1[eb + j]) ? sj * inv_keep : 0.f;
+                else if (dropout_mode == EAV_DROPOUT_PHILOX) sj = ((keep >> j) & 1u) ? sj * inv_keep : 0.f;
+                o[j] = sj;
+            }
+            if (eb >= e0 && eb + 3 < e0 + T4) {
+                *reinterpret_cast<float4 *>(d1 + eb) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (eb + j >= e0 && eb + j < e0 + T4) d1[eb + j] = o[j];
+            }
+        }
+        return;
+    }
     for (int u = lane; u < T4; u += 32) {
         float s = 0.f;
-        if (vec) {
-            const float4 v = *reinterpret_cast<const float4 *>(src + 4 * u);
-            s = elu_f(fmaf(v.x, st.z, st.w)) + elu_f(fmaf(v.y, st.z, st.w)) + elu_f(fmaf(v.z, st.z, st.w)) +
-                elu_f(fmaf(v.w, st.z, st.w));
-        } else {
-            for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[u * P1 + w], st.z, st.w));
-        }
+        for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[u * P1 + w], st.z, st.w));
         s *= invp;
         const int64_t e = row * T4 + u;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[e] ? s * inv_keep : 0.f;
