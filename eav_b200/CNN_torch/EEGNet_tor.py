@@ -29,22 +29,28 @@ class EEGNet_tor(ArenaModule):
 
     def __init__(self, nb_classes, Chans=30, Samples=500, dropoutRate=0.5, kernLength=300, F1=8, D=8, F2=64,
                  norm_rate=1.0, dropoutType='Dropout'):
-        super(EEGNet_tor, self).__init__()
-        # same submodules, same construction order as the reference (EEGNet_tor.py:21-44), so
-        # default initialisation consumes the RNG identically and state_dict keys match
-        self.dropout = nn.Dropout(dropoutRate) if dropoutType == 'Dropout' else nn.Dropout2d(dropoutRate)
-        self.firstConv = nn.Conv2d(1, F1, (1, kernLength), padding='same', bias=False)
-        self.firstBN = nn.BatchNorm2d(F1)
-        self.elu = nn.ELU()
-        self.depthwiseConv = nn.Conv2d(F1, F1 * D, (Chans, 1), groups=F1, padding=0, bias=False)
-        self.depthwiseBN = nn.BatchNorm2d(F1 * D)
-        self.depthwisePool = nn.AvgPool2d((1, 4))
-        self.separableConv = nn.Conv2d(F1 * D, F2, (1, 16), padding='same', bias=False)
-        self.separableBN = nn.BatchNorm2d(F2)
-        self.separablePool = nn.AvgPool2d((1, 8))
-        self.flatten = nn.Flatten()
-        self.dense = nn.Linear(F2 * ((Samples // 4 // 8)), nb_classes)
-        self.softmax = nn.Softmax(dim=1)
+        super().__init__()
+        G, n_feat = F1 * D, F2 * (Samples // 4 // 8)
+        # Attribute name -> module, registered in the reference's order (EEGNet_tor.py:21-44): the state_dict keys
+        # are the attribute names, and the parameterised layers draw their default initialisation from torch's
+        # global RNG in exactly this order.
+        layers = (
+            ("dropout", lambda: (nn.Dropout if dropoutType == 'Dropout' else nn.Dropout2d)(dropoutRate)),
+            ("firstConv", lambda: nn.Conv2d(1, F1, (1, kernLength), padding="same", bias=False)),
+            ("firstBN", lambda: nn.BatchNorm2d(F1)),
+            ("elu", nn.ELU),
+            ("depthwiseConv", lambda: nn.Conv2d(F1, G, (Chans, 1), groups=F1, bias=False)),
+            ("depthwiseBN", lambda: nn.BatchNorm2d(G)),
+            ("depthwisePool", lambda: nn.AvgPool2d((1, 4))),
+            ("separableConv", lambda: nn.Conv2d(G, F2, (1, 16), padding="same", bias=False)),
+            ("separableBN", lambda: nn.BatchNorm2d(F2)),
+            ("separablePool", lambda: nn.AvgPool2d((1, 8))),
+            ("flatten", nn.Flatten),
+            ("dense", lambda: nn.Linear(n_feat, nb_classes)),
+            ("softmax", lambda: nn.Softmax(dim=1)),
+        )
+        for name, ctor in layers:
+            setattr(self, name, ctor())
         self._dims = EegnetDims(nb_classes, Chans=Chans, Samples=Samples, dropoutRate=dropoutRate,
                                 kernLength=kernLength, F1=F1, D=D, F2=F2, norm_rate=norm_rate,
                                 variant=EAV_VARIANT_TOR)
@@ -65,19 +71,16 @@ class Trainer_uni(FusedTrainerMixin):
     index / permutation source so the RNG consumption order matches the reference."""
 
     def __init__(self, model, data, lr=1e-4, batch_size=32, num_epochs=10, device=None):
-        self.lr = lr
-        self.batch_size = batch_size
-        self.num_epochs = num_epochs
-
+        self.lr, self.batch_size, self.num_epochs = lr, batch_size, num_epochs
         self.tr_x, self.tr_y, self.te_x, self.te_y = data
         self.train_dataloader = self._prepare_dataloader(self.tr_x, self.tr_y, shuffle=True)
         self.test_dataloader = self._prepare_dataloader(self.te_x, self.te_y, shuffle=False)
-
         self.model = model
         self.criterion = nn.CrossEntropyLoss()
-        self.optimizer = optim.Adam(self.model.parameters(), lr=self.lr)
-
-        self.device = torch.device(device) if device else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.optimizer = optim.Adam(model.parameters(), lr=lr)
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("eav_b200.Trainer_uni needs a CUDA (B200) device; there is no CPU fallback")
         # nn.DataParallel (EEGNet_tor.py:86-88) is deliberately NOT used: multi-GPU is by subject
@@ -86,31 +89,33 @@ class Trainer_uni(FusedTrainerMixin):
         self._setup_fused(self.model, self.tr_x, self.tr_y, self.te_x, self.te_y)
 
     def _prepare_dataloader(self, x, y, shuffle=False):
-        dataset = TensorDataset(torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32),
-                                torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y, dtype=torch.long))
-        dataloader = DataLoader(dataset, batch_size=self.batch_size, shuffle=shuffle)
-        return dataloader
+        """float32 features / int64 labels -> DataLoader(batch_size, shuffle) (EEGNet_tor.py:91-94); numpy arrays
+        and tensors are both accepted."""
+        def as_t(a, dt):
+            return a.to(dt) if torch.is_tensor(a) else torch.as_tensor(np.asarray(a), dtype=dt)
+        return DataLoader(TensorDataset(as_t(x, torch.float32), as_t(y, torch.long)), batch_size=self.batch_size,
+                          shuffle=shuffle)
 
     def train(self):
         self.model.train()  # once, outside the epoch loop -- as the reference (EEGNet_tor.py:97)
-        for epoch in range(self.num_epochs):
-            n_batches = len(self.train_dataloader)
-            for batch_idx, rows in enumerate(self._index_batches(train=True)):
+        steps_per_epoch = len(self.train_dataloader)
+        for ep in range(1, self.num_epochs + 1):
+            for step, rows in enumerate(self._index_batches(train=True)):
                 loss = self._fused_train_step(rows)
-                if batch_idx % 100 == 0:
-                    print(f"Epoch [{epoch+1}/{self.num_epochs}], Step [{batch_idx}/{n_batches}], Loss: {loss.item():.4f}")
+                if step % 100 == 0:      # the reference's print cadence and format (EEGNet_tor.py:112-113)
+                    print(f"Epoch [{ep}/{self.num_epochs}], Step [{step}/{steps_per_epoch}], Loss: {loss.item():.4f}")
             if self.test_dataloader:
                 self.validate()
 
     def validate(self):
+        """(mean loss, accuracy) over the test set; leaves the model in eval mode like the reference (F5)."""
         self.model.eval()
-        total_loss, total_correct, n_batches = self._fused_validate()
-        avg_loss = total_loss / n_batches
-        accuracy = total_correct / len(self.test_dataloader.dataset)
-        print(f"Validation - Loss: {avg_loss:.4f}, Accuracy: {accuracy:.4f}")
-        return avg_loss, accuracy
+        loss_sum, n_correct, n_batches = self._fused_validate()
+        mean_loss, acc = loss_sum / n_batches, n_correct / len(self.test_dataloader.dataset)
+        print(f"Validation - Loss: {mean_loss:.4f}, Accuracy: {acc:.4f}")
+        return mean_loss, acc
 
 
-def _prepare_dataloader(self, x, y, shuffle=False):   # module-level duplicate kept for signature parity (EEGNet_tor.py:138-141)
-    dataset = TensorDataset(torch.tensor(x, dtype=torch.float32), torch.tensor(y, dtype=torch.long))
-    return DataLoader(dataset, batch_size=self.batch_size, shuffle=shuffle)
+def _prepare_dataloader(self, x, y, shuffle=False):
+    """Module-level twin of Trainer_uni._prepare_dataloader: the reference file defines one too (EEGNet_tor.py:138-141)."""
+    return Trainer_uni._prepare_dataloader(self, x, y, shuffle)
