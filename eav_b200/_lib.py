@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
-                    c_uint64, c_void_p)
+                    c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeav_b200.so")
@@ -64,6 +64,9 @@ SYMBOLS = {
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_mode": (c_int, [c_int, POINTER(c_double), c_void_p]),
+    "eav_peer_exchange_bytes": (c_size_t, [c_size_t]),
+    "eav_peer_allreduce": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_size_t, c_uint32, c_void_p,
+                                  c_uint32, c_void_p]),
     "eav_tc_probe": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int] + [c_int] * 12 + [c_void_p, c_void_p, c_void_p]),
 }
 

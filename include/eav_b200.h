@@ -249,6 +249,25 @@ int eav_measure_fp32_peak_outer(double *tflops, void *stream);
  * register (constant bank); 3: same with Blackwell packed FFMA2 (fma.rn.f32x2). */
 int eav_measure_fp32_peak_mode(int mode, double *tflops, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Peer-memory all-reduce for the large-batch data-parallel driver (BASELINE configs[4]; replaces the
+ * ncclAllReduce calls of the six BatchNorm statistic buffers, the loss and the flat gradient arena that
+ * nn.DataParallel-style training of EEGNet_tor.py:86-88 would need).  One kernel per rank reads the peers' exchange
+ * buffers over NVLink and sums them in rank order, so every rank gets bit-identical results.
+ *   exchange buffer (per rank, mapped into every peer, ZERO-INITIALISED once): eav_peer_exchange_bytes(slot_bytes) bytes
+ *   peer_bases_dev: device array [world] of the exchange buffers' addresses as seen from THIS rank
+ *   call: 1, 2, 3, ... -- the same sequence on every rank; src/dst: n elements (float or double), may alias.
+ *   call_base_dev (optional): device-resident step counter s; the effective call number is s * calls_per_step + call
+ *   with call in 1..calls_per_step, so that a captured CUDA graph of a whole training step replays correctly.
+ * All ranks must issue the same calls in the same order; a rank that never arrives makes the others trap after a
+ * bounded spin instead of hanging. */
+#define EAV_PEER_MAX_WORLD 16
+#define EAV_PEER_MAX_CTAS 64
+size_t eav_peer_exchange_bytes(size_t slot_bytes);
+int eav_peer_allreduce(const void *src, void *dst, int64_t n, int is_f64, const uint64_t *peer_bases_dev,
+                       int world, int rank, size_t slot_bytes, uint32_t call, const int64_t *call_base_dev,
+                       uint32_t calls_per_step, void *stream);
+
 /* Diagnostic for the tcgen05 path: runs reps x ksteps `tcgen05.mma.cta_group::1.kind::tf32` (M x N x 8 each) in one
  * CTA on a caller-supplied shared-memory image (image_floats fp32 words, <= 200 KB) with caller-supplied no-swizzle
  * operand descriptors {byte offset, LBO, SBO, major (0 = K, 1 = MN), byte advance per k-step}; a_bits / b_bits are

@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "rc=$?"; tail -3 gpurun_out/bench_n2.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_n2.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 scripts/large_batch_sweep.py --batches 128,1024,8192 > gpurun_out/sweep_n2.json 2> gpurun_out/sweep.err; tail -1 gpurun_out/sweep.err; cat gpurun_out/sweep_n2.json
+timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -12
+for c in "nccl" "peer" "peer --graph"; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 scripts/large_batch_sweep.py --batches 128,1024,8192 --collective $c 2> gpurun_out/sweep.err | grep '^\[' > gpurun_out/sweep_tmp.json; tail -2 gpurun_out/sweep.err | cut -c1-300; python -c "
+import json; [print(r['collective'], r['cuda_graph'], r['global_batch'], r['bn'], round(r['ms_per_step'],4)) for r in json.load(open('gpurun_out/sweep_tmp.json'))]"
+cp gpurun_out/sweep_tmp.json "gpurun_out/sweep_n2_$(echo $c | tr -d ' -').json"
+done

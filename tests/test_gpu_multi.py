@@ -89,7 +89,7 @@ def test_data_parallel_driver_world1_equals_engine(golden, train):
         assert U.rel_l2(v.numpy(), g[f"{mode}::grad::{k}"]) < TOL, k
 
 
-def _dp_worker(rank, world, port, sd, x, y, m1, m2, q):
+def _dp_worker(rank, world, port, sd, x, y, m1, m2, q, collective="auto"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -103,18 +103,34 @@ def _dp_worker(rank, world, port, sd, x, y, m1, m2, q):
     sl = slice(rank * B, (rank + 1) * B)
     out = {}
     for train in (True, False):
-        dp = DataParallelEEGNet(dims, x.shape[0], lr=1e-3, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES)
+        dp = DataParallelEEGNet(dims, x.shape[0], lr=1e-3, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES,
+                                collective=collective)
+        assert dp.collective == collective, dp.collective
         masks = (m1[sl].cuda().contiguous(), m2[sl].cuda().contiguous()) if train else None
         loss = dp.step(x[sl].cuda().contiguous(), y[sl].cuda().contiguous(), bn_train=train, masks=masks, update=True)
         torch.cuda.synchronize()
         out[train] = (float(loss), dp.grads.cpu(), dp.params.cpu(), dp.bn_state.cpu())
+        for _ in range(3):       # a few more steps: the exchange slots and call numbers are reused
+            dp.step(x[sl].cuda().contiguous(), y[sl].cuda().contiguous(), bn_train=train, masks=masks, update=True)
+        torch.cuda.synchronize()
+        out[(train, "later")] = dp.params.cpu()
+        if collective == "peer":     # whole step as a CUDA graph (peer all-reduce numbered by a device counter)
+            xs, ys = x[sl].cuda().contiguous(), y[sl].cuda().contiguous()
+            a = DataParallelEEGNet(dims, x.shape[0], lr=1e-3, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES, collective="peer", seed=5)
+            b = DataParallelEEGNet(dims, x.shape[0], lr=1e-3, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES, collective="peer", seed=5)
+            for _ in range(4):
+                la = a.step(xs, ys, bn_train=train)
+                lb = b.step(xs, ys, bn_train=train, graph=True)
+            torch.cuda.synchronize()
+            out[(train, "graph")] = (a.params.cpu(), b.params.cpu(), float(la), float(lb))
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
-def test_data_parallel_two_ranks_equal_single_device_global_batch(golden):
+@pytest.mark.parametrize("collective", ["peer", "nccl"])
+def test_data_parallel_two_ranks_equal_single_device_global_batch(golden, collective):
     import torch.multiprocessing as mp
     import gpu_util as U
     from eav_b200.ops import EegnetDims
@@ -127,7 +143,7 @@ def test_data_parallel_two_ranks_equal_single_device_global_batch(golden):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, sd, x, y, m1, m2, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, sd, x, y, m1, m2, q, collective)) for r in range(2)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=300) for _ in procs)
@@ -139,6 +155,12 @@ def test_data_parallel_two_ranks_equal_single_device_global_batch(golden):
         l0, g0, p0, b0 = got[0][train]
         l1, g1, p1, b1 = got[1][train]
         assert l0 == l1 and torch.equal(g0, g1) and torch.equal(p0, p1) and torch.equal(b0, b1)   # replicas stay identical
+        assert torch.equal(got[0][(train, "later")], got[1][(train, "later")])
+        if collective == "peer":
+            for r in (0, 1):
+                pa, pb, la, lb = got[r][(train, "graph")]
+                assert torch.equal(pa, pb) and la == lb          # graph replays == eager steps, bit for bit
+            assert torch.equal(got[0][(train, "graph")][1], got[1][(train, "graph")][1])
         assert abs(l0 - float(g[f"{mode}::loss"])) < TOL * float(g[f"{mode}::loss"])
         gd = U.unpack(dims, g0[0])
         for k, v in gd.items():      # == the reference's single-device gradients at the global batch of 8
