@@ -488,15 +488,18 @@ def main():
                       "fallback: nominal 2250 TF/s bf16 / 2")
         fp32_peak = ops.measure_fp32_peak()
         fp32_ffma2 = ops.measure_fp32_peak(3)
-        tc_on = os.environ.get("EAV_TCONV", "") not in ("ffma", "0")
+        off = ("ffma", "0")
+        tc_all = os.environ.get("EAV_TC", "") not in off
+        tc_on = tc_all and os.environ.get("EAV_TCONV", "") not in off            # temporal conv on tcgen05
+        sc_on = tc_all and os.environ.get("EAV_SEPCONV", "") not in off          # block-2 conv on tcgen05
         conv2 = 2.0 * 64 * 64 * 16 * 125           # block-2 (1,16) conv, flops per sample
         # algorithmic work of each hot kernel, per launch
         model = {
             "tconv_fwd": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
             "tconv_bwd_dw": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
-            "sepconv_fwd": ("fp32", conv2 * N, "flop"),
-            "sepconv_bwd_dx": ("fp32", conv2 * N, "flop"),
-            "sepconv_bwd_dw": ("fp32", conv2 * N, "flop"),
+            "sepconv_fwd": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
+            "sepconv_bwd_dx": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
+            "sepconv_bwd_dw": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
             # y1 + dz1 (8x30x500 each) + y2 + dz2 (64x500 each), fp32
             "dw_bwd": ("hbm", 4.0 * N * (2 * 8 * 30 * 500 + 2 * 64 * 500), "byte"),
             # y1 read + y2 write
@@ -569,11 +572,12 @@ def main():
                        "l2": "no explicit flush: a step streams ~3.5 GB of activations through a 126 MB L2, inputs "
                              "(80 MB batch gathered by index from a 0.7 GB resident set) exceed L2",
                        "parallelism": f"subject-sharded x{world}, no collective", "cuda_graph": True,
-                       "arithmetic": "fp32 storage and accumulation everywhere; the temporal conv (fwd and dW) runs on "
-                                     "tcgen05 as a 3-product tf32 split (hi*hi + hi*lo + lo*hi, ~2^-21 relative), "
-                                     "all other kernels on the fp32 CUDA cores"
-                                     if os.environ.get("EAV_TCONV", "") not in ("ffma", "0") else
-                                     "fp32 CUDA cores everywhere (EAV_TCONV=ffma)"},
+                       "arithmetic": "fp32 storage and accumulation everywhere; the temporal conv and the block-2 conv (fwd, "
+                                     "dX, dW) run on tcgen05 as a 3-product tf32 split (hi*hi + hi*lo + lo*hi, ~2^-21 "
+                                     "relative), all other kernels on the fp32 CUDA cores"
+                                     if all(os.environ.get(k, "") not in ("ffma", "0")
+                                            for k in ("EAV_TC", "EAV_TCONV", "EAV_SEPCONV")) else
+                                     "tensor-core paths (partly) switched off by EAV_TC / EAV_TCONV / EAV_SEPCONV"},
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             ("eval_bn_step" if head_train else "train_bn_step"): {"ms_per_step": other_ms,
