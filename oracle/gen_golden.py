@@ -294,14 +294,78 @@ def gen_legacy():
          filt500_sub=cnt_f[::500, ::7, ::25].copy())
 
 
+def gen_shallow():
+    """Transformer_torch/Transformer_EEG.py ShallowConvNet: the unmodified reference model, imported
+    from /root/reference, forward in eval mode and forward+backward in train mode with its dropouts replaced by
+    recorded masks (torch's own RNG stream, captured with forward hooks)."""
+    import importlib
+    sys.path.insert(0, os.path.join(ref_shim.REF_ROOT, "Transformer_torch"))
+    TE = importlib.import_module("Transformer_EEG")
+    torch.manual_seed(11)
+    model = TE.ShallowConvNet(nb_classes=5)
+    with torch.no_grad():                      # move the parameters off their defaults so every term matters
+        for n, p_ in model.named_parameters():
+            if n.endswith("norm1.bias") or n.endswith("norm2.bias") or n == "bn.bias":
+                p_.normal_(0, 0.1)
+        model.bn.running_mean.normal_(0, 0.2)
+        model.bn.running_var.uniform_(0.5, 1.5)
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 1, 30, 500, generator=g)
+    y = torch.randint(0, 5, (4,), generator=g)
+    out = {"x": x.numpy(), "y": y.numpy()}
+    for k, v in init.items():
+        out["init::" + k] = v.numpy()
+    model.eval()
+    with torch.no_grad():
+        out["eval::probs"] = model(x).numpy()
+    # train mode: record the mask each nn.Dropout applies (output / input where input != 0)
+    model.train()
+    masks = []
+
+    def hook(mod, inp, outp):
+        i = inp[0]
+        m = torch.where(i != 0, outp / torch.where(i != 0, i, torch.ones_like(i)), torch.full_like(i, 2.0) * (outp != 0))
+        # where the input is exactly 0 the mask is unobservable and irrelevant (0 * m = 0); store 0 there
+        masks.append(torch.where(i != 0, m, torch.zeros_like(i)).detach().clone())
+
+    hs = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, torch.nn.Dropout)]
+    torch.manual_seed(5)
+    probs = model(x)
+    loss = torch.nn.CrossEntropyLoss()(probs, y)
+    loss.backward()
+    for h in hs:
+        h.remove()
+    out["train::probs"] = probs.detach().numpy()
+    out["train::loss"] = np.array(float(loss))
+    for i, m in enumerate(masks):
+        out[f"train::mask{i:02d}"] = np.packbits((m != 0).numpy().reshape(-1))
+        out[f"train::mask{i:02d}_shape"] = np.array(m.shape)
+    grads = {n: p_.grad for n, p_ in model.named_parameters()}
+    keep = ["conv.weight", "embedding.value_proj.0.weight", "embedding.value_proj.39.weight", "fc.weight", "bn.weight",
+            "bn.bias"] + [f"transformer.{l}.{n}" for l in (0, 11) for n in
+                          ("attn.W_q.weight", "attn.W_k.weight", "attn.W_v.weight", "norm1.weight", "norm1.bias",
+                           "ffn.net.0.weight", "ffn.net.0.bias", "ffn.net.3.weight", "ffn.net.3.bias", "norm2.weight")]
+    for n in keep:
+        out["train::grad::" + n] = grads[n].numpy()
+    out["train::grad_l2_all"] = np.array([float(grads[n].norm()) for n, _ in model.named_parameters()])
+    out["train::bn_running_mean"] = model.bn.running_mean.numpy()
+    out["train::bn_running_var"] = model.bn.running_var.numpy()
+    save("shallowconvnet_b4.npz", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     if "--only-legacy" in sys.argv:
         gen_legacy()
         sys.exit(0)
+    if "--only-shallow" in sys.argv:
+        gen_shallow()
+        sys.exit(0)
     ns = ref_shim.load()
     gen_preproc(ns)
     gen_legacy()
     gen_eegnet_tor(ns)
     gen_cnn_eeg(ns)
+    gen_shallow()

@@ -207,3 +207,40 @@ def test_cnn_eeg_fwd_bwd_vs_reference(golden, tag, mode):
         # noise (|g| ~ 1e-6): gate on an absolute floor there.
         a, b = params[k].grad.numpy(), g[f"{mode}::grad::{k}"]
         assert rel_l2(a, b) < 5e-5 or np.abs(a - b).max() < 5e-6, k
+
+
+def test_shallowconvnet_oracle_vs_reference(golden):
+    """SURVEY 8f.3 groundwork: oracle/shallow_oracle.py against the unmodified Transformer_EEG.ShallowConvNet
+    (fixture from oracle/gen_golden.py:gen_shallow): eval forward, train forward/loss/backward with the reference's
+    recorded dropout masks, BatchNorm running statistics."""
+    import torch
+    import shallow_oracle as SO
+    g = golden("shallowconvnet_b4.npz")
+    sd = {k[6:]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith("init::")}
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    with torch.no_grad():
+        pe = SO.shallow_forward({k: v.clone() for k, v in sd.items()}, x, train=False)
+    assert np.abs(pe.numpy() - g["eval::probs"]).max() < 2e-6
+    masks = []
+    i = 0
+    while f"train::mask{i:02d}" in g.files:
+        shape = tuple(int(v) for v in g[f"train::mask{i:02d}_shape"])
+        bits = np.unpackbits(g[f"train::mask{i:02d}"])[:int(np.prod(shape))].reshape(shape)
+        masks.append(torch.from_numpy(bits.astype(np.float32)) * 2.0)          # keep / (1 - 0.5)
+        i += 1
+    assert len(masks) == 3 * SO.N_LAYERS + 1
+    tsd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+           for k, v in sd.items()}
+    pt = SO.shallow_forward(tsd, x, train=True, masks=masks)
+    loss = SO.loss_fn(pt, y)
+    loss.backward()
+    assert np.abs(pt.detach().numpy() - g["train::probs"]).max() < 5e-6
+    assert abs(float(loss) - float(g["train::loss"])) < 1e-6
+    for k in g.files:
+        if k.startswith("train::grad::"):
+            ref = g[k]
+            got = tsd[k[len("train::grad::"):]].grad.numpy()
+            denom = max(np.linalg.norm(ref), 1e-8)
+            assert np.linalg.norm(got - ref) / denom < 2e-4, k
+    assert np.allclose(tsd["bn.running_mean"].numpy(), g["train::bn_running_mean"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(tsd["bn.running_var"].numpy(), g["train::bn_running_var"], rtol=1e-5, atol=1e-6)
