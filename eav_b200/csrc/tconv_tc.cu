@@ -399,7 +399,12 @@ __device__ __forceinline__ void split4(float4 v, float4 &h, float4 &l) {
 __device__ __forceinline__ uint64_t desc_mn_sw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return tc::smem_desc(saddr, lbo, sbo) | ((uint64_t)1 << 61);     // layout_type 1 = SWIZZLE_128B_BASE32B
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Barrier among the four epilogue warps only (the other warps keep running): an mbarrier with 128 arrivals per phase.
+__device__ __forceinline__ void epi_sync(uint64_t *bar, uint32_t &phase) {
+    tc::mbar_arrive(bar);
+    tc::mbar_wait(bar, phase);
+    phase ^= 1u;
+}
 
 __global__ void __launch_bounds__(TCW_THREADS, 1)
 tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index,
@@ -409,7 +414,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
     extern __shared__ __align__(1024) float smem[];
     float *ring = smem;                                        // [STAGES][STAGE_FLOATS]
     float *diag = smem + TCW_STAGES * TCW_STAGE_FLOATS;        // [384][33]
-    __shared__ uint64_t bar_full[TCW_STAGES], bar_empty[TCW_STAGES], bar_accfull, bar_accempty;
+    __shared__ uint64_t bar_full[TCW_STAGES], bar_empty[TCW_STAGES], bar_accfull, bar_accempty, bar_epi;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F1 = 8;
@@ -423,6 +428,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
         for (int s = 0; s < TCW_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
         tc::mbar_init(&bar_accfull, 1);
         tc::mbar_init(&bar_accempty, 4);
+        tc::mbar_init(&bar_epi, 128);
         tc::mbar_init_fence();
     }
     if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
@@ -563,6 +569,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
     } else {
         // ---------------- epilogue: D' -> diagonal sums -> partial dW ----------------
         int nu = 0;
+        uint32_t epi_phase = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
             int m, fg, r_lo, r_hi;
             unit_rows(u, m, fg, r_lo, r_hi);
@@ -583,7 +590,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&bar_accempty);
                 }
-                epi_bar();
+                epi_sync(&bar_epi, epi_phase);
                 float *dst = part + (((int64_t)m * S + sp) * F1 + fg * 4 + fl) * K1;
                 for (int k = tid; k < K1; k += 128) {
                     float acc = 0.f;
@@ -592,7 +599,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
                     for (int j = 0; j < 32; ++j) acc += p[j * (TCW_SP + 1)];
                     dst[k] = acc;
                 }
-                epi_bar();
+                epi_sync(&bar_epi, epi_phase);
             }
         }
     }

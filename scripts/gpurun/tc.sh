@@ -1,5 +1,4 @@
 #!/bin/bash
-timeout 300 python scripts/ingest_bench.py --subjects 3 2>&1 | tail -1 | cut -c1-300
-timeout 300 python scripts/train_all_subjects.py --mat-dir /tmp/eav_mat --subjects 3 --epochs 2 2>&1 | tail -1 | cut -c1-500
-timeout 300 python scripts/train_all_subjects.py --mat-dir /tmp/eav_mat --subjects 3 --epochs 2 --legacy-order 2>&1 | tail -1 | cut -c1-500
-timeout 300 python scripts/train_all_subjects.py --subjects 6 --epochs 2 --separable --lr 1e-3 2>&1 | tail -1 | cut -c1-500
+timeout 200 python -m pytest tests/test_gpu_tc.py -m gpu -x -q 2>&1 | tail -2
+timeout 300 compute-sanitizer --tool synccheck --print-limit 5 python -m pytest tests/test_gpu_tc.py -m gpu -q -x -k "matches and (shape4 or shape1)" 2>&1 | grep -E "Barrier error|Device Frame: eav::<unnamed>|ERROR SUMMARY|passed|failed" | sed -E "s/\+0x[0-9a-f]+//" | sort | uniq -c | sort -rn | head -8
+echo "== kbench"; timeout 100 python scripts/kbench.py --stages tconv_bwd_dw 2>&1 | tail -1
