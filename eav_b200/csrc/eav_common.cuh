@@ -57,6 +57,8 @@ __device__ __forceinline__ float elu_f(float x) {
     return x > 0.f ? x : neg;
 }
 __device__ __forceinline__ float elu_grad_from_pre(float x) { return x > 0.f ? 1.f : __expf(x); }
+// ELU for recomputation inside gradient reductions: absolute (not relative) accuracy near zero
+__device__ __forceinline__ float elu_bwd_act(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
 // ---------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = (seed, step).

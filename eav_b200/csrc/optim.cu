@@ -39,15 +39,31 @@ __global__ void adam_graph_kernel(float *__restrict__ p, const float *__restrict
     }
     __syncthreads();
     const float step_size = sh[0], bc2_sqrt = sh[1];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float gi = g[i];
-        float mi = m[i], vi = v[i];
+    auto upd = [&](float gi, float &pi, float &mi, float &vi) {
         mi = mi + (gi - mi) * (1.f - b1);
         vi = vi * b2 + (1.f - b2) * gi * gi;
-        float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
-        m[i] = mi;
-        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        pi = pi - step_size * (mi / denom);
+    };
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+    const int64_t n4 = vec ? n >> 2 : 0;                   // 128-bit part: four arrays, one load each per element group
+    for (int64_t i = tid; i < n4; i += nth) {
+        const float4 g4 = reinterpret_cast<const float4 *>(g)[i];
+        float4 p4 = reinterpret_cast<float4 *>(p)[i], m4 = reinterpret_cast<float4 *>(m)[i], v4 = reinterpret_cast<float4 *>(v)[i];
+        upd(g4.x, p4.x, m4.x, v4.x);
+        upd(g4.y, p4.y, m4.y, v4.y);
+        upd(g4.z, p4.z, m4.z, v4.z);
+        upd(g4.w, p4.w, m4.w, v4.w);
+        reinterpret_cast<float4 *>(p)[i] = p4;
+        reinterpret_cast<float4 *>(m)[i] = m4;
+        reinterpret_cast<float4 *>(v)[i] = v4;
+    }
+    for (int64_t i = 4 * n4 + tid; i < n; i += nth) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        upd(g[i], pi, mi, vi);
+        p[i] = pi; m[i] = mi; v[i] = vi;
     }
 }
 __global__ void counter_inc_kernel(long long *c) { *c += 1; }
