@@ -370,7 +370,7 @@ int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index
 // absolute shared-memory address (scripts/tc_decode.py), so the producers store element e at swz(base + 4 e).
 // D' (M = up to 384 rows in 3 tiles, N = 128 = 4 filters x 32) stays in TMEM for all rows of a work unit
 // (model, filter half, row range); the epilogue sums the 32 diagonals through shared memory.
-// Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-12 producers (BatchNorm-1 backward is applied to
+// Roles: warps 0-3 epilogue, warp 4 MMA issue, warps 5-11 producers, one ring stage each (BatchNorm-1 backward is applied to
 // dz1 while staging, then the tf32 hi/lo split).
 // =============================================================================================
 namespace {
