@@ -2,23 +2,40 @@
 """bench.py -- EEGNet train samples/sec (fwd+bwd+step) and preprocessing GB/s on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload subjects|cnn_eeg|large_batch]
 
-Workload (BASELINE.json configs[2], the one the metric is quoted on): the reference's 42
-per-subject EEGNet_tor models (Chans=30, Samples=500, kernLength=300, F1=8, D=8, F2=64, 5
-classes, Adam lr=1e-5, batch 32) trained in lock-step on synthetic EEG of the dataset's shape
-(200 x 10000 x 30 per subject).  One "step" = one batch of 32 for each of the 42 models =
-1344 samples through forward + loss + backward + Adam.  Raw synthetic EEG is generated on the
-device, preprocessed by the CUDA FIR/SOS/epoch pipeline (timed separately: `preprocess`),
-split 280/120 with the reference's index logic, and the training set stays resident in HBM.
-With N > 1 every rank holds its own 42 subjects (weak scaling, no data-path collective:
-subjects are independent); `value` is the aggregate over ranks, time = max over ranks.
+Default workload (BASELINE.json configs[2], the one the metric is quoted on): the reference's 42
+per-subject EEGNet_tor models (Chans=30, Samples=500, kernLength=300, F1=8, D=8, F2=64, 5 classes,
+Adam lr=1e-5, batch 32) on synthetic EEG of the dataset's shape (200 x 10000 x 30 per subject).
+The 42 subjects are SHARDED over the N GPUs exactly as SURVEY 8e says -- subject s on rank
+(s-1) % N, i.e. 6,6,5,5,5,5,5,5 at N=8 -- with no data-path collective, so the total work is fixed
+("scaling": "strong") and the time is the makespan (max over ranks).  Every rank preprocesses its own
+subjects' raw recordings with the CUDA FIR/SOS/epoch pipeline (timed separately: `preprocess`), splits
+280/120 with the reference's index logic and keeps both sets resident in HBM.
 
-`--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the
-reference is Python and /root/reference does not exist on the GPU box) on the host cores.
+A "step" is one optimisation step of the reference's real epoch loop (Trainer_uni.train(),
+EEGNet_tor.py:96-135) for every model: per epoch a fresh shuffle, 8 batches of 32 and the ragged
+batch of 24 (drop_last=False), then the validation pass over the 120 test epochs.  The timed K steps
+run in that order (whole epochs are ONE CUDA graph each, eav_b200.trainer_core.EpochRunner; the
+K % 9 left-over steps are per-step graphs); samples/s counts TRAINING samples only, the validation
+passes inside the timed region are overhead, as they are for the reference.  BatchNorm mode follows the
+reference: epoch 1 in train mode (runs in the warm-up, reported as `first_epoch`), every later epoch
+in eval mode (validate() leaves the model in eval mode and nothing switches back).
+
+`--workload cnn_eeg` (configs[3]) runs the CNN_EEG.EEGNet variant at the EAV shape through the same
+loop (its trainer calls model.train() every epoch: train-mode BN + dropout, Adam lr=1e-3);
+`--workload large_batch` (configs[4]) the single-model large-batch sweep with the batch split over the
+ranks and the BN sums / gradient arena all-reduced (NCCL and the peer-memory kernel).
+
+`--impl reference` times the reference's own CPU implementation on the host cores: the stock
+EEGNet_tor + Trainer_uni objects from oracle/_ref/ (verbatim copies made by oracle/make_ref.py in the
+build container; kind "reference"), or the oracle port when that copy is absent (kind "port").
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -34,22 +51,33 @@ sys.path.insert(0, ROOT)
 METRIC = "EEGNet train samples/sec (fwd+bwd+step)"
 N_SUBJECTS, BATCH, N_TRAIN, N_TEST = 42, 32, 280, 120
 FLOP_PER_SAMPLE = 198.9e6          # fwd 90.3 + bwd 108.6 MFLOP (conv/dense MACs only)
+FLOP_PER_SAMPLE_CNN = 153.6e6      # the CNN_EEG variant at the EAV shape
 TCONV_FLOP_PER_SAMPLE = 72.0e6     # 2*K1*F1*Chans*Samples = 2*300*8*30*500, fwd; identical for dW1
 PREPROC_BYTES_PER_SUBJECT = 264e6  # 240 MB raw f32 read once + 24 MB epochs written once
+WORKLOAD_TOR = ("EEGNet_tor per-subject training of the 42 synthetic subjects (BASELINE.json configs[2]): Chans=30 "
+                "Samples=500 kernLength=300 F1=8 D=8 F2=64, 5 classes, batch 32, Adam lr=1e-5, 280/120 split; the "
+                "reference's epoch loop (9 steps incl. the ragged batch of 24, then validation)")
+WORKLOAD_CNN = ("CNN_EEG.EEGNet variant at the EAV shape (BASELINE.json configs[3]): Chans=30 Samples=500 "
+                "kernLength=300 F1=8 D=8 F2=64 (depthwise-temporal + pointwise block 2, logits), 5 classes, batch 32, "
+                "Adam lr=1e-3, 42 subjects, EEGNetTrainer's epoch loop (train-mode BN + dropout every epoch)")
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=90)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--subjects", type=int, default=N_SUBJECTS, help="subject models per GPU")
-    ap.add_argument("--bn-mode", default="train", choices=["train", "eval"],
-                    help="BN mode of the headline step (the other mode is reported beside it)")
+    ap.add_argument("--workload", default="subjects", choices=["subjects", "cnn_eeg", "large_batch"])
+    ap.add_argument("--subjects", type=int, default=N_SUBJECTS, help="subjects in TOTAL (sharded over the GPUs)")
+    ap.add_argument("--bn-mode", default="reference", choices=["reference", "train", "eval"],
+                    help="BatchNorm mode of the timed epochs: 'reference' = what the reference's trainer does "
+                         "(EEGNet_tor: eval mode after epoch 1, SURVEY F5; CNN_EEG: train mode every epoch)")
     ap.add_argument("--no-preproc", action="store_true", help="skip the preprocessing leg (epochs drawn N(0,1))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the per-kernel stage timing")
+    ap.add_argument("--no-replica", action="store_true", help="skip the replica_throughput leg (N > 1)")
+    ap.add_argument("--batches", default="32,128,512,2048,8192", help="large_batch: global batch sizes")
     return ap.parse_args()
 
 
@@ -134,32 +162,148 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_train_baseline(steps, warmup, bn_train=True):
-    """The CPU restatement of the reference's Trainer step (oracle/eegnet_oracle.py) on the host
-    cores: B=32 steps of ONE subject model (1/42 of a GPU step)."""
+# ----------------------------------------------------------------------------- CPU arm
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _synthetic_split(seed, n_tr=N_TRAIN, n_te=N_TEST):
+    """One subject's worth of model inputs of the benchmark's shape (values N(0,1): CPU time is data independent)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    trx = torch.randn(n_tr, 1, 30, 500, generator=g)
+    tex = torch.randn(n_te, 1, 30, 500, generator=g)
+    return [trx.numpy(), torch.randint(0, 5, (n_tr,), generator=g).numpy(),
+            tex.numpy(), torch.randint(0, 5, (n_te,), generator=g).numpy()]
+
+
+def _pick_threads(step_fn, candidates):
+    """The thread count that steps fastest (the 32-core box of round 1 was SLOWER with all threads)."""
+    import torch
+    best, best_t = None, 1e30
+    for n in candidates:
+        torch.set_num_threads(n)
+        step_fn()
+        t0 = time.perf_counter()
+        step_fn(); step_fn()
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
+def cpu_train_reference(steps, warmup, variant="tor", schedule="reference"):
+    """K optimisation steps of ONE subject model on the host cores, in the reference's epoch order (8 x 32 + 24, then
+    validate()).  Uses the STOCK reference objects when oracle/_ref (or /root/reference) is present: model,
+    DataLoaders, criterion, optimizer and validate() are the reference's own (through the three mechanical shims of
+    oracle/ref_shim.py); only the five-line loop body of Trainer_uni.train() (EEGNet_tor.py:99-110) is restated so
+    that exactly K steps can be timed.  Otherwise the oracle port.  Returns a dict."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
-    import eegnet_oracle as EO
-    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
-    try:        # every host core this process may use (torchrun pins OMP_NUM_THREADS=1 otherwise)
-        torch.set_num_threads(len(os.sched_getaffinity(0)))
-    except Exception:
-        pass
-    torch.manual_seed(1)
-    sd = EEGNet_tor(5).state_dict()
-    params, buffers = EO.split_state(sd, "tor")
-    opt = EO.Adam(params, lr=1e-5)
-    g = torch.Generator().manual_seed(0)
-    x = torch.randn(BATCH, 1, 30, 500, generator=g)
-    y = torch.randint(0, 5, (BATCH,), generator=g)
-    for _ in range(warmup):
-        EO.train_step("tor", params, buffers, opt, x, y, bn_train)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        EO.train_step("tor", params, buffers, opt, x, y, bn_train)
-    dt = time.perf_counter() - t0
-    return BATCH * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+    import ref_shim
+    cores = _host_threads()
+    cand = sorted({c for c in (4, 8, 16, 32, cores) if c <= cores} or {cores})
+    data = _synthetic_split(1)
+    n_train_samples = 0
+    if variant == "tor" and ref_shim.available():
+        ns = ref_shim.load()
+        torch.manual_seed(1)
+        model = ref_shim.make_eegnet_tor(ns, nb_classes=5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr = ns.EEGNet_tor.Trainer_uni(model, data=data, lr=1e-5, batch_size=BATCH, num_epochs=1,
+                                           device=torch.device("cpu"))
+
+        def one_step(batch):
+            d, t = batch
+            d, t = d.to(tr.device), t.to(tr.device)
+            scores = tr.model(d)
+            loss = tr.criterion(scores, t)
+            tr.optimizer.zero_grad()
+            loss.backward()
+            tr.optimizer.step()
+            return loss
+
+        first = next(iter(tr.train_dataloader))
+        tr.model.train()
+        threads = _pick_threads(lambda: one_step(first), cand)
+        with contextlib.redirect_stdout(io.StringIO()):
+            done = 0
+            while done < max(1, warmup):                     # warm-up: epoch 1, train mode, then validate() -> eval mode
+                for b in tr.train_dataloader:
+                    one_step(b); done += 1
+            if schedule == "reference":
+                tr.validate()
+            elif schedule == "eval":
+                tr.model.eval()
+            else:
+                tr.model.train()
+            t0 = time.perf_counter()
+            done = 0
+            while done < steps:
+                for b in tr.train_dataloader:
+                    one_step(b)
+                    n_train_samples += b[0].shape[0]
+                    done += 1
+                    if done == steps:
+                        break
+                else:
+                    tr.validate()
+                    if schedule == "train":
+                        tr.model.train()
+            dt = time.perf_counter() - t0
+        kind = "reference"
+        what = ("stock EEGNet_tor + Trainer_uni objects of the unmodified reference (oracle/_ref via oracle/ref_shim.py), "
+                "torch-CPU")
+    else:
+        import eegnet_oracle as EO
+        if variant == "tor":
+            from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor as Net
+            kw, lr = {}, 1e-5
+        else:
+            from eav_b200.CNN_torch.CNN_EEG import EEGNet as Net
+            kw, lr = dict(Chans=30, Samples=500, kernLength=300, F1=8, D=8, F2=64), 1e-3
+        torch.manual_seed(1)
+        sd = Net(5, **kw).state_dict()
+        params, buffers = EO.split_state(sd, variant)
+        opt = EO.Adam(params, lr=lr)
+        x_all, y_all = torch.from_numpy(data[0]), torch.from_numpy(data[1]).long()
+        tex, tey = torch.from_numpy(data[2]), torch.from_numpy(data[3]).long()
+        train_mode = [True]
+
+        def one_step(rows):
+            EO.train_step(variant, params, buffers, opt, x_all[rows], y_all[rows], train_mode[0])
+
+        def validate():
+            with torch.no_grad():
+                for b0 in range(0, N_TEST, BATCH):
+                    EO.loss_fn(EO.forward(variant, params, buffers, tex[b0:b0 + BATCH], False), tey[b0:b0 + BATCH])
+
+        threads = _pick_threads(lambda: one_step(torch.arange(BATCH)), cand)
+        for _ in range(max(1, warmup)):
+            one_step(torch.arange(BATCH))
+        train_mode[0] = (schedule == "train") or (schedule == "reference" and variant == "cnn")
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps:
+            perm = torch.randperm(N_TRAIN)
+            for b0 in range(0, N_TRAIN, BATCH):
+                rows = perm[b0:b0 + BATCH]
+                one_step(rows)
+                n_train_samples += rows.numel()
+                done += 1
+                if done == steps:
+                    break
+            else:
+                validate()
+        dt = time.perf_counter() - t0
+        kind = "port"
+        what = "oracle/eegnet_oracle.py (torch-CPU restatement of the reference model / trainer)"
+    return {"value": n_train_samples / dt, "ms_per_step": dt / steps * 1e3, "cores": threads, "kind": kind,
+            "host_cores": cores, "thread_candidates": cand, "what": what, "steps": steps}
 
 
 def cpu_preproc_baseline():
@@ -179,35 +323,40 @@ def run_reference(args):
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
     budget_steps = min(steps, 60)
-    v, ms, threads = cpu_train_baseline(budget_steps, min(warmup, 3), bn_train=args.bn_mode == "train")
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "EEGNet_tor per-subject training, Chans=30 Samples=500 kernLength=300 F1=8 D=8 F2=64, "
-                                   "5 classes, Adam lr=1e-5, batch 32", "bn_mode": args.bn_mode,
-                       "note": "each timed step = one B=32 train step of ONE subject model on the host cores"},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{budget_steps} B=32 train steps (fwd+bwd+Adam, {args.bn_mode}-mode BN) of one subject model; "
-                                       "oracle/eegnet_oracle.py restatement of CNN_torch/EEGNet_tor.py on torch-CPU"},
-            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    variant = "cnn" if args.workload == "cnn_eeg" else "tor"
+    r = cpu_train_reference(budget_steps, min(warmup, 9), variant=variant, schedule=args.bn_mode)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_CNN if variant == "cnn" else WORKLOAD_TOR, "bn_mode": args.bn_mode,
+                       "note": "CPU arm: the subjects train one after another on the host, so the whole-job rate equals "
+                               "the rate of ONE subject model; each timed step = one B=32 (or ragged 24) step of one "
+                               f"model, {budget_steps} steps in the reference's epoch order with validate() after each "
+                               "epoch, warm-up = epoch 1 in train mode"},
+            "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                             "host_cores": r["host_cores"], "thread_candidates": r["thread_candidates"],
+                             "sample": f"{budget_steps} train steps of one subject model (280 train / 120 test epochs of "
+                                       f"30x500): {r['what']}"},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
 
-# ----------------------------------------------------------------------------- B200 arm
-def synth_raw_device(S, seed, device):
+# ----------------------------------------------------------------------------- B200 arm helpers
+def synth_raw_device(subjects, device):
     """Synthetic raw EEG on the device, dataset shape [S][200][30][10000] f32 (SURVEY 8d recipe:
-    N(0,1) + 0.5 sin(2 pi 50 t) + 5 sin(2 pi 0.1 t), t continuous across trials) + one-hot labels."""
+    N(0,1) + 0.5 sin(2 pi 50 t) + 5 sin(2 pi 0.1 t), t continuous across trials) + one-hot labels.
+    Seeded by SUBJECT id, so a subject's recording does not depend on the sharding."""
     import torch
-    g = torch.Generator(device=device).manual_seed(seed)
+    S = len(subjects)
     raw = torch.empty(S, 200, 30, 10000, dtype=torch.float32, device=device)
     t = (torch.arange(200 * 10000, device=device, dtype=torch.float64) / 500.0).reshape(200, 1, 10000)
     wave = (0.5 * torch.sin(2 * np.pi * 50.0 * t) + 5.0 * torch.sin(2 * np.pi * 0.1 * t)).float()
-    for s in range(S):
-        raw[s].normal_(generator=g)
-        raw[s] += wave
     labels = []
-    for s in range(S):
-        rng = np.random.default_rng(1000 + seed * 1000 + s)
+    for i, s in enumerate(subjects):
+        g = torch.Generator(device=device).manual_seed(1000 + s)
+        raw[i].normal_(generator=g)
+        raw[i] += wave
+        rng = np.random.default_rng(1000 + s)
         cls = rng.permutation(np.repeat(np.arange(10), 20))
         lab = np.zeros((10, 200))
         lab[cls, np.arange(200)] = 1.0
@@ -232,48 +381,139 @@ def _emit(line):
     _REAL_STDOUT.flush()
 
 
-def main():
-    args = parse()
-    _claim_stdout()
-    if args.impl == "reference":
-        return run_reference(args)
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
+
+class Dist:
+    """torch.distributed plumbing of one rank (one process per GPU, NCCL)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize()
+
+    def max(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+            self.dist.destroy_process_group()
+
+
+def dp_parity_check(D):
+    """World >= 2 only: the large-batch data-parallel step (BN sums + gradient arena all-reduced over NVLink) against
+    the reference-generated single-device golden at the GLOBAL batch of 8 (tests/golden/eegnet_tor_b8.npz) -- the same
+    assertion as tests/test_gpu_multi.py::test_data_parallel_two_ranks_equal_single_device_global_batch, run here
+    because the driver's GPU test tier has one GPU.  Returns a small record for the JSON line."""
     import torch
-    import torch.distributed as dist
+    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
+    from eav_b200.data_parallel import DataParallelEEGNet
+    from eav_b200.ops import EegnetDims
+    if D.world < 2 or 8 % D.world:
+        return None
+    g = np.load(os.path.join(ROOT, "tests", "golden", "eegnet_tor_b8.npz"), allow_pickle=False)
+    sd = {k[6:]: torch.from_numpy(np.array(g[k])) for k in g.files if k.startswith("init::")}
+    dims = EegnetDims(5)
+    n, layout = dims.param_layout()
+    B = 8 // D.world
+    sl = slice(D.rank * B, (D.rank + 1) * B)
+    x = torch.from_numpy(g["x"]).reshape(8, 30, 500)[sl].contiguous().to(D.dev)
+    y = torch.from_numpy(g["y"])[sl].contiguous().to(D.dev)
+    m1 = torch.from_numpy(g["mask1"]).reshape(8, 64, 125)[sl].contiguous().to(D.dev)
+    m2 = torch.from_numpy(g["mask2"]).reshape(8, 64, 15)[sl].contiguous().to(D.dev)
+    rec = {"world": D.world, "global_batch": 8, "golden": "tests/golden/eegnet_tor_b8.npz (unmodified reference, one device)"}
+    worst = 0.0
+    for coll in ("nccl", "peer"):
+        for train in (True, False):
+            mode = "train" if train else "eval"
+            try:
+                dp = DataParallelEEGNet(dims, 8, lr=1e-3, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES, collective=coll)
+                loss = dp.step(x, y, bn_train=train, masks=(m1, m2) if train else None, update=False)
+                torch.cuda.synchronize()
+                err = abs(float(loss) - float(g[f"{mode}::loss"])) / abs(float(g[f"{mode}::loss"]))
+                row = dp.grads[0].detach().cpu()
+                for name, off, shape in layout:
+                    a = row[off:off + int(np.prod(shape))].double().numpy().reshape(-1)
+                    b = np.asarray(g[f"{mode}::grad::{name}"], dtype=np.float64).reshape(-1)
+                    nb = np.linalg.norm(b)
+                    err = max(err, float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a - b)))
+                ident = torch.tensor([float(row.double().sum())], dtype=torch.float64, device=D.dev)
+                lo, hi = ident.clone(), ident.clone()
+                D.dist.all_reduce(lo, op=D.dist.ReduceOp.MIN)
+                D.dist.all_reduce(hi, op=D.dist.ReduceOp.MAX)
+                rec[f"{coll}_{mode}"] = {"max_rel_err": err, "replicas_identical": bool(lo.item() == hi.item())}
+                worst = max(worst, err)
+                del dp
+            except Exception as e:  # noqa: BLE001
+                rec[f"{coll}_{mode}"] = {"error": repr(e)[:200]}
+                worst = float("inf")
+    rec["tolerance"] = 1e-4
+    rec["ok"] = bool(D.max(worst) < 1e-4)
+    return rec
+
+
+# ----------------------------------------------------------------------------- per-subject training workloads
+def run_subject_workload(args, variant):
+    import ctypes
+    import torch
     from eav_b200 import _lib, ops
     from eav_b200.Dataload_eeg import decimation_taps, epoch_slots
     from eav_b200.EAV_datasplit import EAVDataSplit
-    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
+    from eav_b200.sharding import shard_sizes, subjects_for_rank
     from eav_b200.trainer_core import SubjectBatchTrainer
     from scipy.signal import butter
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    D = Dist()
+    world, rank, local, dev = D.world, D.rank, D.local, D.dev
     _lib.require_device()
     lib = _lib.load()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    M, B, K, W = args.subjects, BATCH, args.steps, max(3, args.warmup)
-
-    def barrier():
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    tor = variant == "tor"
+    if tor:
+        from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor as Net
+        net_kw, lr, flop_per_sample = {}, 1e-5, FLOP_PER_SAMPLE
+    else:
+        from eav_b200.CNN_torch.CNN_EEG import EEGNet as Net
+        net_kw, lr, flop_per_sample = dict(Chans=30, Samples=500, kernLength=300, F1=8, D=8, F2=64), 1e-3, FLOP_PER_SAMPLE_CNN
+    S_total, B, K, W = args.subjects, BATCH, max(1, args.steps), max(3, args.warmup)
+    mine = subjects_for_rank(range(1, S_total + 1), rank, world)
+    M = len(mine)
+    if M == 0:
+        raise SystemExit(f"rank {rank}: no subject to train ({S_total} subjects over {world} ranks)")
+    rows_per_model = N_TRAIN + N_TEST
+    peaks = _peaks()
 
     # ---------------------------------------------------------------- data: raw -> preprocess -> split
     pre = None
     if not args.no_preproc:
-        raw, labels = synth_raw_device(M, rank, dev)
+        raw, labels = synth_raw_device(mine, dev)
         taps = decimation_taps(5)
         sos = butter(5, [0.5, 45], btype="bandpass", fs=100, output="sos")
         plans = [epoch_slots(l) for l in labels]
@@ -286,201 +526,278 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 3
-        barrier()
+        D.barrier()
         e0.record()
         for _ in range(reps):
             eng.run(raw, taps, sos, slot, 400, epochs=epochs)
         e1.record()
         torch.cuda.synchronize()
-        pre_ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-        hbm_peak = None
-        try:
-            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-            peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        except Exception:
+        pre_ms_local = e0.elapsed_time(e1) / reps
+        pre_ms = D.max(pre_ms_local)
+        hbm_peak = peaks.get("hbm_gbs")
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        if hbm_peak is None:
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        gbs = PREPROC_BYTES_PER_SUBJECT * M / (pre_ms * 1e-3) / 1e9
-        pre = {"metric": "preprocess HBM GB/s (filter/decimate/epoch)", "value": gbs * world, "unit": "GB/s",
-               "ms": pre_ms, "subjects_per_gpu": M, "launches": int(pre_launches),
-               "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                            "traffic": None, "peak_source": peak_src,
-                            "algorithmic_bytes": PREPROC_BYTES_PER_SUBJECT * M}}
-        # the legacy order (band-pass at 500 Hz over the raw recording, then decimate: CNN_EEG_tf.py:64-75,180-189) on
-        # a bounded number of subjects (it needs one more raw-sized buffer); reported beside the shipped order
+        gbs_rank = PREPROC_BYTES_PER_SUBJECT * M / (pre_ms_local * 1e-3) / 1e9
+        traffic = None
         try:
-            from scipy.signal import butter as _butter
-            ML = min(M, 8)
-            eng2 = ops.PreprocEngine(ML, device=dev, order=1)
-            sos500 = _butter(5, [3, 50], btype="band", fs=500, output="sos")
-            ep2 = torch.empty(ML, 400, 30, 500, dtype=torch.float32, device=dev)
-            eng2.run(raw[:ML], taps, sos500, slot[:ML].contiguous(), 400, epochs=ep2)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("preprocess")
+        except Exception:
+            pass
+        pre = {"metric": "preprocess HBM GB/s (filter/decimate/epoch)",
+               "value": PREPROC_BYTES_PER_SUBJECT * S_total / (pre_ms * 1e-3) / 1e9, "unit": "GB/s",
+               "ms": pre_ms, "subjects_total": S_total, "subjects_this_rank": M, "launches": int(pre_launches),
+               "roofline": {"bound": "hbm", "achieved": gbs_rank, "peak": hbm_peak, "unit": "GB/s", "frac": gbs_rank / hbm_peak,
+                            "traffic": traffic, "peak_source": peak_src, "ms_this_rank": pre_ms_local,
+                            "algorithmic_bytes": PREPROC_BYTES_PER_SUBJECT * M}}
+        if world == 1 and M >= 8:
+            # the legacy order (band-pass at 500 Hz over the raw recording, then decimate: CNN_EEG_tf.py:64-75,180-189)
+            # on a bounded number of subjects (it needs one more raw-sized buffer); reported beside the shipped order
+            try:
+                ML = 8
+                eng2 = ops.PreprocEngine(ML, device=dev, order=1)
+                sos500 = butter(5, [3, 50], btype="band", fs=500, output="sos")
+                ep2 = torch.empty(ML, 400, 30, 500, dtype=torch.float32, device=dev)
                 eng2.run(raw[:ML], taps, sos500, slot[:ML].contiguous(), 400, epochs=ep2)
-            e1.record()
-            torch.cuda.synchronize()
-            lms = e0.elapsed_time(e1) / reps
-            # raw read twice (state pass, apply pass) + filtered written and read + decimated written and read + epochs
-            lbytes = ML * (4 * 240e6 + 2 * 48e6 + 24e6)
-            pre["bandpass_first_order"] = {"ms": lms, "subjects": ML, "ms_per_subject": lms / ML,
-                                           "algorithmic_bytes": lbytes, "achieved_gbs": lbytes / (lms * 1e-3) / 1e9,
-                                           "frac_of_hbm_peak": lbytes / (lms * 1e-3) / 1e9 / hbm_peak}
-            del eng2, ep2
-        except Exception as e:  # noqa: BLE001
-            pre["bandpass_first_order"] = {"error": repr(e)}
-        # labels {1,3,5,7,9} -> 0..4 (harness remap) and the reference's 280/120 split
-        tr_rows, tr_y = [], []
-        for s in range(M):
-            y = (plans[s][1] - 1) // 2
-            tri, _ = EAVDataSplit(np.zeros((400, 1)), y).get_split_indices(h_idx=56)
-            tr_rows.append(torch.from_numpy(tri + 400 * s))
-            tr_y.append(torch.from_numpy(y[tri]))
-        rows = torch.cat(tr_rows).to(dev)
-        x_train = epochs.reshape(M * 400, 30, 500).index_select(0, rows).contiguous()
-        y_train = torch.cat(tr_y).to(dev)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(reps):
+                    eng2.run(raw[:ML], taps, sos500, slot[:ML].contiguous(), 400, epochs=ep2)
+                e1.record()
+                torch.cuda.synchronize()
+                lms = e0.elapsed_time(e1) / reps
+                # raw read twice (state pass, apply pass) + filtered written and read + decimated written and read + epochs
+                lbytes = ML * (4 * 240e6 + 2 * 48e6 + 24e6)
+                pre["bandpass_first_order"] = {"ms": lms, "subjects": ML, "ms_per_subject": lms / ML,
+                                               "algorithmic_bytes": lbytes, "achieved_gbs": lbytes / (lms * 1e-3) / 1e9,
+                                               "frac_of_hbm_peak": lbytes / (lms * 1e-3) / 1e9 / hbm_peak}
+                del eng2, ep2
+            except Exception as e:  # noqa: BLE001
+                pre["bandpass_first_order"] = {"error": repr(e)}
+        # labels {1,3,5,7,9} -> 0..4 (harness remap) and the reference's 280/120 split;
+        # resident layout per subject: [280 train rows][120 test rows]
+        sel, ys = [], []
+        for i in range(M):
+            y = (plans[i][1] - 1) // 2
+            tri, tei = EAVDataSplit(np.zeros((400, 1)), y).get_split_indices(h_idx=56)
+            assert len(tri) == N_TRAIN and len(tei) == N_TEST
+            sel.append(torch.from_numpy(np.concatenate([tri, tei]) + 400 * i))
+            ys.append(torch.from_numpy(np.concatenate([y[tri], y[tei]])))
+        x_all = epochs.reshape(M * 400, 30, 500).index_select(0, torch.cat(sel).to(dev)).contiguous()
+        y_all = torch.cat(ys).to(dev)
         del raw, epochs, eng
         torch.cuda.empty_cache()
     else:
         g = torch.Generator(device=dev).manual_seed(rank)
-        x_train = torch.randn(M * N_TRAIN, 30, 500, generator=g, device=dev)
-        y_train = torch.randint(0, 5, (M * N_TRAIN,), generator=g, device=dev)
+        x_all = torch.randn(M * rows_per_model, 30, 500, generator=g, device=dev)
+        y_all = torch.randint(0, 5, (M * rows_per_model,), generator=g, device=dev)
 
     # ---------------------------------------------------------------- models
-    dims = ops.EegnetDims(5)
-    tr = SubjectBatchTrainer(dims, M, x_train, y_train, lr=1e-5, max_batch=B, seed=1234 + rank)
-    sds = []
-    for s in range(M):
-        torch.manual_seed(1 + s + 1000 * rank)
-        sds.append(EEGNet_tor(5).state_dict())
-    tr.load_state_dicts(sds, EEGNet_tor._BN_NAMES)
+    sds, dims = [], None
+    for s in mine:
+        torch.manual_seed(s)                                 # the reference seeds each subject's model by itself
+        mdl = Net(5, **net_kw)
+        dims = mdl._dims
+        sds.append(mdl.state_dict())
+    tr = SubjectBatchTrainer(dims, M, x_all, y_all, lr=lr, max_batch=B, seed=1234)
+    tr.load_state_dicts(sds, Net._BN_NAMES)
+    runner = tr.epoch_runner(N_TRAIN, N_TEST, B, rows_per_model=rows_per_model, subject_ids=mine, max_epochs=4096,
+                             seed=20261017)
+    sizes = runner.train_sizes                               # [32]*8 + [24]
+    spe = len(sizes)                                         # steps per epoch
+    steady_train = (args.bn_mode == "train") or (args.bn_mode == "reference" and not tor)
 
-    # index schedule: per model a fresh permutation per epoch, 8 full batches of 32 per epoch
-    n_sched = W + K + 8
-    gen = torch.Generator().manual_seed(7 + rank)
-    sched = torch.empty(n_sched, M * B, dtype=torch.int32)
-    perms = None
-    for i in range(n_sched):
-        if i % 8 == 0:
-            perms = torch.stack([torch.randperm(N_TRAIN, generator=gen) for _ in range(M)])
-        b = i % 8
-        sched[i] = (perms[:, b * B:(b + 1) * B] + torch.arange(M).unsqueeze(1) * N_TRAIN).reshape(-1).int()
-    sched = sched.to(dev)
-
-    def timed_steps(bn_train, n_warm, n_steps):
-        for i in range(n_warm):
-            tr.train_step(sched[i], bn_train=bn_train)
-        barrier()
+    def timed(fn):
+        D.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(n_steps):
-            tr.train_step(sched[n_warm + i], bn_train=bn_train)
+        fn()
         e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1) / n_steps)
+        D.barrier()
+        return D.max(e0.elapsed_time(e1))
 
-    head_train = args.bn_mode == "train"
-    # the other BN mode first (short), then the headline run with the clock sampler on
-    other_ms = timed_steps(not head_train, 3, min(K, 10))
+    def run_steps(n, bn_train):
+        """n optimisation steps in epoch order: whole epochs as one graph each, the rest as per-step graphs."""
+        full, rem = divmod(n, spe)
+        for _ in range(full):
+            runner.run_epoch(bn_train)
+        if rem:
+            runner.enqueue_schedule()
+            for s in range(rem):
+                tr.train_step(runner.step_index(s), bn_train=bn_train)
+        return full * N_TRAIN + sum(sizes[:rem])             # training samples per model
+
+    # warm-up: epoch 1 in train mode (graph capture + replay), an eager steady-state epoch (counts the launches),
+    # the steady-state graph, and the per-step graphs the K % 9 left-over steps need
+    runner.run_epoch(True)
+    first_ms = timed(lambda: run_steps(spe, True))           # one more train-mode epoch, timed: `first_epoch`
     l0 = lib.eav_launch_count()
-    tr.use_graph = False
-    tr.program(B, head_train, "train").graph = None
-    tr.train_step(sched[0], bn_train=head_train)
+    runner.run_epoch(steady_train, use_graph=False)
     torch.cuda.synchronize()
-    launches_per_step = int(lib.eav_launch_count() - l0)
-    tr.use_graph = True
+    launches_per_epoch = int(lib.eav_launch_count() - l0)
+    runner.run_epoch(steady_train)
+    rem = K % spe
+    launches_rem = 0
+    if rem:
+        tr.use_graph = False
+        l0 = lib.eav_launch_count()
+        runner.enqueue_schedule()
+        for s in range(rem):
+            tr.train_step(runner.step_index(s), bn_train=steady_train)
+        torch.cuda.synchronize()
+        launches_rem = int(lib.eav_launch_count() - l0)
+        tr.use_graph = True
+        run_steps(rem, steady_train)
+    warm_steps = 4 * spe + 2 * rem
+    while warm_steps < W:
+        run_steps(spe, steady_train)
+        warm_steps += spe
+    torch.cuda.synchronize()
+
     clocks = ClockSampler(local)
     clocks.start()
-    ms = timed_steps(head_train, W, K)
+    samples_per_model = [0]
+    total_ms = timed(lambda: samples_per_model.__setitem__(0, run_steps(K, steady_train)))
     clk = clocks.stop()
-    value = world * M * B / (ms * 1e-3)
-    loss_now = tr.program(B, head_train, "train").loss.float().mean().item()
+    ms = total_ms / K
+    samples_total = S_total * samples_per_model[0]           # every subject walks the same schedule shape
+    value = samples_total / (total_ms * 1e-3)
+    hist = runner.results()
+    loss_now = float(hist[-1, :, 0].mean()) if hist.shape[0] else None
+    gpu_launches = (K // spe) * launches_per_epoch + launches_rem
 
     # ---------------------------------------------------------------- end-to-end: host buffers in, loss out
-    p = tr.host_step_program(B, bn_train=head_train)
+    # Same K steps (+ the validation batches after each 9th), but every batch starts in pinned HOST memory:
+    # H2D on a copy stream into a double-buffered staging area, per-step graphs through the C ABI, loss D2H per step.
     n_ring = 4
     host_x = [torch.empty(M * B, 30, 500, dtype=torch.float32).pin_memory() for _ in range(n_ring)]
     host_y = [torch.empty(M * B, dtype=torch.int64).pin_memory() for _ in range(n_ring)]
     for r in range(n_ring):
-        host_x[r].copy_(x_train.index_select(0, sched[r].long()).cpu())
-        host_y[r].copy_(y_train.index_select(0, sched[r].long()).cpu())
+        rows = torch.randint(0, M * rows_per_model, (M * B,), device=dev)
+        host_x[r].copy_(x_all.index_select(0, rows).cpu())
+        host_y[r].copy_(y_all.index_select(0, rows).cpu())
     host_loss = torch.empty(M, dtype=torch.float32).pin_memory()
-    stage_x = [p.x_src, torch.empty_like(p.x_src)]
-    stage_y = [p.y_src, torch.empty_like(p.y_src)]
+    host_corr = torch.empty(M, dtype=torch.int32).pin_memory()
+    stage_x = [torch.empty(M * B, 30, 500, dtype=torch.float32, device=dev) for _ in range(2)]
+    stage_y = [torch.empty(M * B, dtype=torch.int64, device=dev) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
+    items = []                                               # (kind, batch) in the reference's loop order
+    for i in range(K):
+        items.append(("train", sizes[i % spe]))
+        if i % spe == spe - 1:
+            items += [("eval", Bv) for Bv in runner.val_sizes]
+    progs = {}
+    for kind, Bs in set(items):
+        for slot_i in range(2):
+            progs[(kind, Bs, slot_i)] = tr.host_step_program(Bs, bn_train=steady_train and kind == "train", kind=kind,
+                                                             x_src=stage_x[slot_i], y_src=stage_y[slot_i], slot=slot_i)
+    h2d_total = [0]
 
-    def e2e_steps(n):
+    def e2e_steps(items):
         ev_copied = [torch.cuda.Event() for _ in range(2)]
         ev_used = [torch.cuda.Event() for _ in range(2)]
+        h2d_total[0] = 0
+
+        def copy_in(i, slot_i):
+            n = M * items[i][1]
+            stage_x[slot_i][:n].copy_(host_x[i % n_ring][:n], non_blocking=True)
+            stage_y[slot_i][:n].copy_(host_y[i % n_ring][:n], non_blocking=True)
+            h2d_total[0] += n * (30 * 500 * 4 + 8)
+
         with torch.cuda.stream(copy_stream):
-            stage_x[0].copy_(host_x[0], non_blocking=True); stage_y[0].copy_(host_y[0], non_blocking=True)
+            copy_in(0, 0)
             ev_copied[0].record(copy_stream)
-        for i in range(n):
+        for i, (kind, Bs) in enumerate(items):
             cur, nxt = i & 1, (i + 1) & 1
-            if i + 1 < n:                                   # H2D of step i+1 overlaps the kernels of step i
+            if i + 1 < len(items):                          # H2D of item i+1 overlaps the kernels of item i
                 with torch.cuda.stream(copy_stream):
                     if i >= 1:
                         copy_stream.wait_event(ev_used[nxt])
-                    stage_x[nxt].copy_(host_x[(i + 1) % n_ring], non_blocking=True)
-                    stage_y[nxt].copy_(host_y[(i + 1) % n_ring], non_blocking=True)
+                    copy_in(i + 1, nxt)
                     ev_copied[nxt].record(copy_stream)
             main_stream.wait_event(ev_copied[cur])
-            p.x_src, p.y_src = stage_x[cur], stage_y[cur]
-            p.enqueue()
+            p = progs[(kind, Bs, cur)]
+            p.run()
             ev_used[cur].record(main_stream)
             host_loss.copy_(p.loss, non_blocking=True)      # D2H of the step's result
+            if kind == "eval":
+                host_corr.copy_(p.ncorrect, non_blocking=True)
         torch.cuda.synchronize()
 
-    e2e_steps(3)
-    barrier()
+    e2e_steps(items[:min(len(items), 2 * spe + 8)])          # warm-up: captures the per-(batch, kind, slot) graphs
+    D.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    e2e_steps(K)
+    e2e_steps(items)
     e1.record()
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / K)
-    e2e_value = world * M * B / (e2e_ms * 1e-3)
-    h2d = M * B * (30 * 500 * 4 + 8)
+    e2e_total_ms = D.max(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3))
+    e2e_value = samples_total / (e2e_total_ms * 1e-3)
+    h2d_per_step = D.sum(h2d_total[0]) / K
+    d2h_per_step = D.sum(4 * M * len(items) + 4 * M * sum(1 for k, _ in items if k == "eval")) / K
+
+    # ---------------------------------------------------------------- replica throughput (N > 1): 42 subjects on EVERY GPU
+    replica = None
+    if world > 1 and not args.no_replica:
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        MR = S_total
+        xr = torch.randn(MR * 64, 30, 500, generator=g, device=dev)
+        yr = torch.randint(0, 5, (MR * 64,), generator=g, device=dev)
+        trr = SubjectBatchTrainer(dims, MR, xr, yr, lr=lr, max_batch=B, seed=99)
+        trr.load_state_dicts([sds[i % M] for i in range(MR)], Net._BN_NAMES)
+        idx = (torch.arange(MR).unsqueeze(1) * 64 + torch.arange(B).unsqueeze(0)).reshape(-1).int().to(dev)
+        for _ in range(3):
+            trr.train_step(idx, bn_train=steady_train)
+        n_rep = 10
+        rms = timed(lambda: [trr.train_step(idx, bn_train=steady_train) for _ in range(n_rep)]) / n_rep
+        replica = {"value": world * MR * B / (rms * 1e-3), "unit": "samples/s", "ms_per_step": rms,
+                   "subjects_per_gpu": MR, "samples_per_step": world * MR * B,
+                   "note": "round 1's headline, kept for comparison only: every GPU holds ALL 42 subject models "
+                           "(independent replicas, N x the work, N(0,1) inputs) -- replica throughput, not the "
+                           "42-subject workload"}
+        del trr, xr, yr
 
     # ---------------------------------------------------------------- per-kernel timing (roofline of the dominant kernel)
-    stages, roof = None, None
-    if not args.no_stages:
-        import ctypes
-        prog = tr.program(B, head_train, "train")
-        cfg = prog.cfg()
-        prog.graph = None
-        prog.enqueue()                                      # leaves a complete forward/backward in the workspace
-        torch.cuda.synchronize()
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        n_st = lib.eav_eegnet_stage_count()
-        stages = {}
-        reps = 5
-        for s_id in range(n_st):
-            name = lib.eav_eegnet_stage_name(s_id).decode()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stages, roof, stages_other = None, None, None
+    if not args.no_stages and rank == 0:
+        def stage_times(bn_train):
+            prog = tr.program(B, bn_train, "train")
+            cfg = prog.cfg()
+            keep = prog.idx
+            prog.idx = torch.arange(M * B, dtype=torch.int32, device=dev) % N_TRAIN + \
+                (torch.arange(M * B, device=dev) // B * rows_per_model).int()
+            g_keep, prog.graph = prog.graph, None
+            prog.enqueue()                                  # leaves a complete forward/backward in the workspace
+            torch.cuda.synchronize()
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            out = {}
+            reps = 5
+            for s_id in range(lib.eav_eegnet_stage_count()):
+                name = lib.eav_eegnet_stage_name(s_id).decode()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-            def go():
-                _lib.check(lib.eav_eegnet_run_stage(ctypes.byref(cfg), s_id, ops._ptr(tr.x), ops._ptr(prog.idx),
-                                                    ops._ptr(tr.params), ops._ptr(tr.bn_state), None, None,
-                                                    ops._ptr(prog.out), ops._ptr(prog.dout), ops._ptr(tr.grads),
-                                                    ops._ptr(tr.workspace), tr.ws_bytes, st), "run_stage")
-            go()
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(reps):
+                def go():
+                    _lib.check(lib.eav_eegnet_run_stage(ctypes.byref(cfg), s_id, ops._ptr(tr.x), ops._ptr(prog.idx),
+                                                        ops._ptr(tr.params), ops._ptr(tr.bn_state), None, None,
+                                                        ops._ptr(prog.out), ops._ptr(prog.dout), ops._ptr(tr.grads),
+                                                        ops._ptr(tr.workspace), tr.ws_bytes, st), "run_stage")
                 go()
-            b.record()
-            torch.cuda.synchronize()
-            stages[name] = a.elapsed_time(b) / reps
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(reps):
+                    go()
+                b.record()
+                torch.cuda.synchronize()
+                out[name] = a.elapsed_time(b) / reps
+            prog.idx, prog.graph = keep, g_keep
+            return out
+
+        stages = stage_times(steady_train)
+        stages_other = stage_times(not steady_train)
         tot = sum(stages.values())
         N = M * B
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         hbm_peak = peaks.get("hbm_gbs", 7700.0)
         # dense tf32 runs at half the bf16 rate on tcgen05 (kind::tf32 consumes K=8 per 32 B, kind::f16 K=16)
         tf32_peak = peaks.get("bf16_tflops", 2250.0) / 2
@@ -491,24 +808,28 @@ def main():
         off = ("ffma", "0")
         tc_all = os.environ.get("EAV_TC", "") not in off
         tc_on = tc_all and os.environ.get("EAV_TCONV", "") not in off            # temporal conv on tcgen05
-        sc_on = tc_all and os.environ.get("EAV_SEPCONV", "") not in off          # block-2 conv on tcgen05
+        sc_on = tc_all and os.environ.get("EAV_SEPCONV", "") not in off and tor  # block-2 conv on tcgen05
         conv2 = 2.0 * 64 * 64 * 16 * 125           # block-2 (1,16) conv, flops per sample
-        # algorithmic work of each hot kernel, per launch
+        # ALGORITHMIC work of each hot kernel per launch.  For the two HBM-bound block-1
+        # kernels that is what the step cannot avoid moving once y1 is saved for backward: y1 is written by
+        # tconv_fwd, so dw_fwd's compulsory traffic is the y2 write only (+ y1 if it is not fused into the conv
+        # epilogue), dw_bwd's is one y1 read + dz2 (+ y2 in train mode); the dz1 round trip is NOT algorithmic.
         model = {
             "tconv_fwd": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
             "tconv_bwd_dw": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
-            "sepconv_fwd": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
-            "sepconv_bwd_dx": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
-            "sepconv_bwd_dw": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
-            # y1 + dz1 (8x30x500 each) + y2 + dz2 (64x500 each), fp32
-            "dw_bwd": ("hbm", 4.0 * N * (2 * 8 * 30 * 500 + 2 * 64 * 500), "byte"),
-            # y1 read + y2 write
+            "dw_bwd": ("hbm", 4.0 * N * (8 * 30 * 500 + 64 * 500 * (2 if steady_train else 1)), "byte"),
             "dw_fwd": ("hbm", 4.0 * N * (8 * 30 * 500 + 64 * 500), "byte"),
         }
+        if tor:
+            model.update({"sepconv_fwd": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
+                          "sepconv_bwd_dx": ("tensor" if sc_on else "fp32", conv2 * N, "flop"),
+                          "sepconv_bwd_dw": ("tensor" if sc_on else "fp32", conv2 * N, "flop")})
 
         def kernel_roofline(name):
             bound, work, kind = model[name]
             t = stages[name] * 1e-3
+            if t <= 0:
+                return None
             if kind == "flop":
                 ach, unit = work / t / 1e12, "TFLOP/s"
                 pk = tf32_peak if bound == "tensor" else fp32_peak
@@ -519,8 +840,8 @@ def main():
                     "ms_per_launch": stages[name], "share_of_step": stages[name] / tot,
                     ("algorithmic_flops_per_launch" if kind == "flop" else "algorithmic_bytes_per_launch"): work}
 
-        per_kernel = {k: kernel_roofline(k) for k in model}
-        dom = max(model, key=lambda k: stages[k])
+        per_kernel = {k: v for k, v in ((k, kernel_roofline(k)) for k in model) if v is not None}
+        dom = max(per_kernel, key=lambda k: stages[k])
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
@@ -536,67 +857,210 @@ def main():
             "hbm": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 7.7 TB/s nominal",
         }[roof["bound"]]
         roof["kernels"] = per_kernel
+        roof["stage_models"] = M
         roof["fp32_ceilings"] = {"ffma_pipe_peak": fp32_peak, "register_outer_product_ffma2": fp32_ffma2,
                                  "note": "CUDA-core ceilings on this device: immediate-operand FFMA loop, and an 8x8 "
-                                         "register outer product with packed FFMA2 (the block-2 conv kernels' mix)"}
-        roof["whole_step"] = {"achieved": FLOP_PER_SAMPLE * N / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                              "note": "algorithmic conv/dense flops of fwd+bwd over the measured step time"}
+                                         "register outer product with packed FFMA2"}
+        roof["whole_step"] = {"achieved": flop_per_sample * samples_total / (total_ms * 1e-3) / 1e12 / world,
+                              "unit": "TFLOP/s per GPU",
+                              "note": "algorithmic conv/dense flops of fwd+bwd over the measured time of the K steps "
+                                      "(validation passes included in the time, not in the flops)"}
+
+    # ---------------------------------------------------------------- multi-GPU correctness of the large-batch mode
+    dp_rec = dp_parity_check(D) if world > 1 else None
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cms, threads = cpu_train_baseline(12, 2, bn_train=head_train)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"12 B=32 train steps ({args.bn_mode}-mode BN) of one subject model = 1/42 of a GPU step; "
-                         "oracle/eegnet_oracle.py (torch-CPU restatement of CNN_torch/EEGNet_tor.py)",
-               "ms_per_step": cms}
+        r = cpu_train_reference(12, 3, variant=variant, schedule=args.bn_mode)
+        cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+               "host_cores": r["host_cores"],
+               "sample": f"12 train steps of ONE of the 42 subject models (the CPU trains them one after another, so its "
+                         f"whole-job rate is this rate): {r['what']}",
+               "ms_per_step": r["ms_per_step"]}
         if pre is not None:
             pv, pdt = cpu_preproc_baseline()
             pre["cpu_baseline"] = {"value": pv, "unit": "GB/s", "cores": 1, "kind": "port",
                                    "sample": f"1 of 42 subjects (264 MB algorithmic), oracle/preproc_oracle.c, {pdt:.2f} s"}
 
-    if world > 1:
-        dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
+    D.close()
     if rank != 0:
         return
+    mode_txt = ("train-mode BN + dropout every epoch" if steady_train else
+                "eval-mode BN, no dropout (the reference's epochs 2..N, SURVEY F5); epoch 1 (train mode) ran in the warm-up "
+                "and is reported as first_epoch")
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{M} per-subject EEGNet_tor models per GPU trained in lock-step "
-                                   "(BASELINE.json configs[2]): Chans=30 Samples=500 kernLength=300 F1=8 D=8 F2=64, "
-                                   "5 classes, batch 32 per model, Adam lr=1e-5; synthetic 200x10000x30 EEG per subject "
-                                   "preprocessed on the GPU, 280/120 split",
-                       "subjects_per_gpu": M, "batch_per_model": B, "samples_per_step": M * B * world,
-                       "bn_mode": args.bn_mode, "dropout": "on-device Philox" if head_train else "off (eval)",
-                       "l2": "no explicit flush: a step streams ~3.5 GB of activations through a 126 MB L2, inputs "
-                             "(80 MB batch gathered by index from a 0.7 GB resident set) exceed L2",
-                       "parallelism": f"subject-sharded x{world}, no collective", "cuda_graph": True,
+            "config": {"workload": WORKLOAD_TOR if tor else WORKLOAD_CNN,
+                       "subjects_total": S_total, "subjects_per_gpu": shard_sizes(S_total, world),
+                       "batch_per_model": B, "steps_per_epoch": spe, "batch_sizes": sizes,
+                       "validation_batches_per_epoch": runner.val_sizes,
+                       "train_samples_in_timed_region": samples_total, "bn_mode": args.bn_mode, "bn_mode_timed": mode_txt,
+                       "warmup_steps_actual": warm_steps,
+                       "l2": "no explicit flush: a step streams > 0.4 GB of activations per 6 subjects through a 126 MB "
+                             "L2 and gathers its batch by index from a resident set larger than L2",
+                       "parallelism": f"42 subjects sharded over {world} GPU(s), subject s on rank (s-1) % N, no "
+                                      "collective on the data path; time = max over ranks (makespan)",
+                       "cuda_graph": "one graph per epoch (device-side shuffle, 9 train steps, 4 validation batches)",
                        "arithmetic": "fp32 storage and accumulation everywhere; the temporal conv and the block-2 conv (fwd, "
                                      "dX, dW) run on tcgen05 as a 3-product tf32 split (hi*hi + hi*lo + lo*hi, ~2^-21 "
                                      "relative), all other kernels on the fp32 CUDA cores"
                                      if all(os.environ.get(k, "") not in ("ffma", "0")
                                             for k in ("EAV_TC", "EAV_TCONV", "EAV_SEPCONV")) else
                                      "tensor-core paths (partly) switched off by EAV_TC / EAV_TCONV / EAV_SEPCONV"},
-            "gpu_launches": launches_per_step * K,
-            "launches_per_step": launches_per_step,
-            ("eval_bn_step" if head_train else "train_bn_step"): {"ms_per_step": other_ms,
-                                                                   "value": world * M * B / (other_ms * 1e-3),
-                                                                   "unit": "samples/s"},
-            "final_mean_loss": loss_now,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": M * 4,
-                    "how": "pinned host batch -> cudaMemcpyAsync (double-buffered on a copy stream) -> "
-                           "eav_eegnet_forward/loss/backward/adam through the C ABI -> loss D2H every step"},
+            "gpu_launches": gpu_launches,
+            "launches_per_epoch": launches_per_epoch,
+            "first_epoch": {"ms_per_step": first_ms / spe, "value": S_total * N_TRAIN / (first_ms * 1e-3),
+                            "unit": "samples/s", "note": "one epoch in train-mode BN + on-device Philox dropout "
+                                                         "(9 steps + validation), the reference's epoch 1"},
+            "final_mean_train_loss": loss_now,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_total_ms / K,
+                    "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                    "how": "the same K steps (+ validation batches) with every batch in pinned host memory: "
+                           "cudaMemcpyAsync on a copy stream into a double-buffered staging area -> "
+                           "eav_eegnet_forward/loss/backward/adam through the C ABI (per-step CUDA graphs) -> loss "
+                           "(and #correct) D2H every step; bytes are summed over all ranks"},
             "clocks": clk}
+    if replica is not None:
+        line["replica_throughput"] = replica
+    if dp_rec is not None:
+        line["dp_parity"] = dp_rec
     if roof is not None:
         line["roofline"] = roof
         line["stage_ms"] = stages
+        line["stage_ms_other_bn_mode"] = stages_other
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if pre is not None:
         line["preprocess"] = pre
     _emit(line)
+
+
+# ----------------------------------------------------------------------------- configs[4]: large-batch sweep
+def run_large_batch(args):
+    """One EEGNet_tor model, global batch split over the ranks, BN sums + loss + the 300 KB gradient arena all-reduced
+    (eav_b200.data_parallel).  Headline = the largest batch in train mode with the faster collective; every
+    (batch, BN mode, collective) point is listed with the collective's share of the step."""
+    import torch
+    from eav_b200 import _lib
+    from eav_b200.CNN_torch.EEGNet_tor import EEGNet_tor
+    from eav_b200.data_parallel import DataParallelEEGNet
+    from eav_b200.ops import EegnetDims
+
+    D = Dist()
+    world, rank, local, dev = D.world, D.rank, D.local, D.dev
+    _lib.require_device()
+    lib = _lib.load()
+    K, W = max(1, args.steps), max(3, args.warmup)
+    torch.manual_seed(0)
+    sd = EEGNet_tor(5).state_dict()
+    batches = [int(b) for b in args.batches.split(",") if int(b) % world == 0]
+    colls = ["none"] if world == 1 else ["nccl", "peer"]
+    points, best = [], None
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches = 0
+    for GB in batches:
+        Bl = GB // world
+        g = torch.Generator(device=dev).manual_seed(rank)
+        x = torch.randn(Bl, 30, 500, generator=g, device=dev)
+        y = torch.randint(0, 5, (Bl,), generator=g, device=dev)
+        hx, hy = x.cpu().pin_memory(), y.cpu().pin_memory()
+        for mode in ("train", "eval"):
+            solo_ms = None
+            for coll in colls:
+                try:
+                    dp = DataParallelEEGNet(EegnetDims(5), GB, lr=1e-5, state_dict=sd, bn_names=EEGNet_tor._BN_NAMES,
+                                            collective="auto" if coll == "none" else coll)
+                except Exception as e:  # noqa: BLE001
+                    points.append({"global_batch": GB, "bn": mode, "collective": coll, "error": repr(e)[:160]})
+                    continue
+                graph = coll in ("peer", "none")
+                l0 = lib.eav_launch_count()
+                dp.step(x, y, bn_train=mode == "train", graph=False)
+                per_step_launches = int(lib.eav_launch_count() - l0)
+                for _ in range(W):
+                    dp.step(x, y, bn_train=mode == "train", graph=graph)
+                D.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(K):
+                    loss = dp.step(x, y, bn_train=mode == "train", graph=graph)
+                e1.record()
+                D.barrier()
+                ms = D.max(e0.elapsed_time(e1) / K)
+                # the same step with the collectives switched off (dp_world kept, so the kernels are identical):
+                # the difference is the collective's share
+                if world > 1 and solo_ms is None:
+                    keep = dp._allreduce
+                    dp._allreduce = lambda t: None
+                    for _ in range(3):
+                        dp.step(x, y, bn_train=mode == "train", graph=False)
+                    D.barrier()
+                    e0.record()
+                    for _ in range(K):
+                        dp.step(x, y, bn_train=mode == "train", graph=False)
+                    e1.record()
+                    D.barrier()
+                    solo_ms = D.max(e0.elapsed_time(e1) / K)
+                    dp._allreduce = keep
+                # end to end: the rank's slice of the batch from pinned host memory every step, loss D2H
+                hl = torch.empty(1).pin_memory()
+                D.barrier()
+                t0 = time.perf_counter()
+                for _ in range(K):
+                    x.copy_(hx, non_blocking=True); y.copy_(hy, non_blocking=True)
+                    loss = dp.step(x, y, bn_train=mode == "train", graph=graph)
+                    hl.copy_(loss.reshape(1), non_blocking=True)
+                torch.cuda.synchronize()
+                e2e_ms = D.max((time.perf_counter() - t0) * 1e3 / K)
+                pt = {"global_batch": GB, "per_gpu_batch": Bl, "bn": mode, "collective": coll, "cuda_graph": graph,
+                      "ms_per_step": ms, "samples_per_s": GB / ms * 1e3, "e2e_ms_per_step": e2e_ms,
+                      "e2e_samples_per_s": GB / e2e_ms * 1e3, "launches_per_step": per_step_launches,
+                      "loss": float(loss)}
+                if solo_ms is not None:
+                    pt["eager_ms_without_collectives"] = solo_ms
+                    if not graph:
+                        pt["collective_share_of_step"] = max(0.0, 1.0 - solo_ms / ms)
+                points.append(pt)
+                if mode == "train" and (best is None or GB > best["global_batch"] or
+                                        (GB == best["global_batch"] and ms < best["ms_per_step"])):
+                    best = pt
+                    launches = per_step_launches * K
+                del dp
+    clk = clocks.stop()
+    dp_rec = dp_parity_check(D) if world > 1 else None
+    D.close()
+    if rank != 0:
+        return
+    Bl = best["per_gpu_batch"]
+    line = {"metric": METRIC, "value": best["samples_per_s"], "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "large-batch synthetic EEGNet_tor sweep (BASELINE.json configs[4]): ONE model, global batch "
+                                   f"{args.batches} split over the ranks, train-mode BN sums + loss + the 300 KB gradient "
+                                   "arena all-reduced every step (NCCL, and the one-kernel peer-memory all-reduce)",
+                       "headline_point": {k: best[k] for k in ("global_batch", "per_gpu_batch", "bn", "collective", "cuda_graph")},
+                       "parallelism": f"dp{world}", "l2": "inputs of the large points exceed L2 (8192 x 60 KB = 492 MB)"},
+            "gpu_launches": launches, "sweep": points,
+            "e2e": {"value": best["e2e_samples_per_s"], "unit": "samples/s", "ms_per_step": best["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": world * Bl * (30 * 500 * 4 + 8), "d2h_bytes_per_step": 4 * world,
+                    "how": "each rank copies its slice of the batch from pinned host memory every step, loss D2H"},
+            "clocks": clk}
+    if dp_rec is not None:
+        line["dp_parity"] = dp_rec
+    _emit(line)
+
+
+def main():
+    args = parse()
+    _claim_stdout()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "large_batch":
+        return run_large_batch(args)
+    return run_subject_workload(args, "cnn" if args.workload == "cnn_eeg" else "tor")
 
 
 if __name__ == "__main__":

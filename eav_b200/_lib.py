@@ -60,6 +60,11 @@ SYMBOLS = {
                               c_float, c_void_p]),
     "eav_adam_step_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
                                     c_float, c_float, c_void_p]),
+    "eav_epoch_schedule": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_int64, c_uint64, c_void_p,
+                                   c_void_p]),
+    "eav_epoch_accumulate": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "eav_epoch_commit": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                 c_void_p]),
     "eav_renorm_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),

@@ -92,6 +92,12 @@ class _Program:
         self.core.step_dev.copy_(step_before)
         torch.cuda.synchronize()
 
+    def run(self):
+        """launch(), capturing the CUDA graph on first use when the trainer uses graphs."""
+        if self.graph is None and self.core.use_graph and self.mask1 is None:
+            self.capture()
+        self.launch()
+
     def launch(self):
         if self.graph is not None:
             self.graph.replay()
@@ -215,17 +221,164 @@ class SubjectBatchTrainer:
         p.launch()
         return p.loss, p.ncorrect, p.out
 
+    def epoch_runner(self, n_train, n_test, batch, rows_per_model=None, train_first_row=0, test_first_row=None,
+                     subject_ids=None, max_epochs=1024, seed=None):
+        """Whole-epoch CUDA graphs over this trainer's resident rows (see EpochRunner)."""
+        return EpochRunner(self, n_train, n_test, batch, rows_per_model, train_first_row, test_first_row,
+                           subject_ids, max_epochs, seed)
+
     # -------------------------------------------------------- host-fed steps (end-to-end path)
-    def host_step_program(self, B, bn_train=True):
-        """A train program whose batch comes from a device staging buffer filled by H2D copies
-        (what the reference does every step, EEGNet_tor.py:100-101) instead of resident rows."""
-        key = (B, bool(bn_train), "host")
+    def host_step_program(self, B, bn_train=True, kind="train", x_src=None, y_src=None, slot=0):
+        """A program whose batch comes from a device staging buffer filled by H2D copies (what the
+        reference does every step, EEGNet_tor.py:100-101, and every validation batch, :124-125) instead
+        of resident rows.  x_src / y_src: caller-owned staging buffers (>= M*B rows); `slot`
+        distinguishes programs bound to different buffers of a double-buffered staging area."""
+        key = (B, bool(bn_train), "host", kind, slot)
         p = self._programs.get(key)
         if p is None:
-            p = _Program(self, B, bool(bn_train), "train")
+            p = _Program(self, B, bool(bn_train), kind)
             d = self.dims
-            p.x_src = torch.empty(self.M * B, d.Chans, d.Samples, dtype=torch.float32, device=self.device)
-            p.y_src = torch.empty(self.M * B, dtype=torch.int64, device=self.device)
+            p.x_src = x_src if x_src is not None else torch.empty(self.M * B, d.Chans, d.Samples, dtype=torch.float32,
+                                                                  device=self.device)
+            p.y_src = y_src if y_src is not None else torch.empty(self.M * B, dtype=torch.int64, device=self.device)
             p.use_x_index = False
             self._programs[key] = p
         return p
+
+class EpochRunner:
+    """One CUDA graph = one epoch of Trainer_uni.train() (EEGNet_tor.py:96-116) for all M models:
+    a fresh on-device permutation (eav_epoch_schedule), ceil(n_train/batch) train steps including
+    the ragged last batch (drop_last=False, EEGNet_tor.py:92-93), the validation pass over the
+    n_test rows (EEGNet_tor.py:118-135) and the per-epoch loss / accuracy bookkeeping -- no host
+    work, no H2D copy and no synchronisation between steps.  The host replays one graph per epoch
+    and reads the [epochs][M][3] history (mean train loss, mean validation loss, validation
+    accuracy) once at the end.
+
+    Row layout of core.x / core.y: model m's training rows are train_first_row + m*rows_per_model
+    + [0, n_train), its test rows test_first_row + m*rows_per_model + [0, n_test).
+    Two graphs exist at most: train-mode BN + dropout (the reference's epoch 1) and
+    eval-mode BN (every later epoch).
+    """
+
+    def __init__(self, core, n_train, n_test, batch, rows_per_model=None, train_first_row=0, test_first_row=None,
+                 subject_ids=None, max_epochs=1024, seed=None):
+        self.core, self.n_train, self.n_test, self.batch = core, int(n_train), int(n_test), int(batch)
+        self.rows_per_model = int(rows_per_model if rows_per_model is not None else n_train + n_test)
+        self.train_first_row = int(train_first_row)
+        self.test_first_row = int(test_first_row if test_first_row is not None else train_first_row + n_train)
+        self.max_epochs = int(max_epochs)
+        self.seed = int(core.seed if seed is None else seed) & (2 ** 64 - 1)
+        if batch > core.max_batch:
+            raise ValueError(f"batch {batch} > max_batch {core.max_batch}")
+        dev, M = core.device, core.M
+        self.train_sizes = [min(batch, n_train - b0) for b0 in range(0, n_train, batch)]
+        self.val_sizes = [min(batch, n_test - b0) for b0 in range(0, n_test, batch)]
+        self.sched = torch.zeros(max(1, len(self.train_sizes)), M * batch, dtype=torch.int32, device=dev)
+        ids = torch.arange(M) if subject_ids is None else torch.as_tensor(list(subject_ids))
+        if ids.numel() != M:
+            raise ValueError("subject_ids must have one entry per model")
+        self.subject_ids = ids.to(torch.int32).to(dev)
+        base = (torch.arange(M) * self.rows_per_model + self.test_first_row).unsqueeze(1)
+        self.val_idx = []
+        for v, Bv in enumerate(self.val_sizes):
+            cols = torch.arange(v * batch, v * batch + Bv).unsqueeze(0)
+            self.val_idx.append((base + cols).reshape(-1).to(torch.int32).to(dev))
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.train_acc = torch.zeros(M, 2, dtype=torch.float64, device=dev)
+        self.val_acc = torch.zeros(M, 2, dtype=torch.float64, device=dev)
+        self.history = torch.zeros(self.max_epochs, M, 3, dtype=torch.float32, device=dev)
+        self._graphs = {}
+
+    # ------------------------------------------------------------------------------
+    def step_index(self, s):
+        """x_index vector of train step s of the CURRENT schedule buffer (device view, [M*B_s])."""
+        M, B = self.core.M, self.batch
+        return self.sched[s, :M * self.train_sizes[s]]
+
+    def enqueue_schedule(self, sched=None, epoch_dev=None):
+        c = self.core
+        sched = self.sched if sched is None else sched
+        epoch_dev = self.epoch_dev if epoch_dev is None else epoch_dev
+        _lib.check(c.lib.eav_epoch_schedule(_ptr(sched), _ptr(self.subject_ids), c.M, self.n_train, self.batch,
+                                            self.rows_per_model, self.train_first_row, self.seed, _ptr(epoch_dev),
+                                            _stream()), "eav_epoch_schedule")
+
+    def peek_schedule(self, epoch):
+        """Host copy of the index schedule of `epoch` (list of int32 CPU tensors, one per step)."""
+        tmp = torch.zeros_like(self.sched)
+        e = torch.tensor([int(epoch)], dtype=torch.int64, device=self.core.device)
+        self.enqueue_schedule(tmp, e)
+        M = self.core.M
+        return [tmp[s, :M * Bs].cpu() for s, Bs in enumerate(self.train_sizes)]
+
+    def enqueue(self, bn_train):
+        """Issue one whole epoch on the current stream (kernel launches only: capturable)."""
+        c, lib = self.core, self.core.lib
+        self.enqueue_schedule()
+        for s, Bs in enumerate(self.train_sizes):
+            p = c.program(Bs, bn_train, "train")
+            keep = p.idx
+            p.idx = self.step_index(s)
+            try:
+                p.enqueue()
+            finally:
+                p.idx = keep
+            _lib.check(lib.eav_epoch_accumulate(_ptr(p.loss), None, c.M, _ptr(self.train_acc), _stream()),
+                       "eav_epoch_accumulate")
+        for v, Bv in enumerate(self.val_sizes):
+            p = c.program(Bv, False, "eval")
+            keep = p.idx
+            p.idx = self.val_idx[v]
+            try:
+                p.enqueue()
+            finally:
+                p.idx = keep
+            _lib.check(lib.eav_epoch_accumulate(_ptr(p.loss), _ptr(p.ncorrect), c.M, _ptr(self.val_acc), _stream()),
+                       "eav_epoch_accumulate")
+        _lib.check(lib.eav_epoch_commit(_ptr(self.train_acc), _ptr(self.val_acc), c.M, len(self.train_sizes),
+                                        len(self.val_sizes), self.n_test, _ptr(self.history), self.max_epochs,
+                                        _ptr(self.epoch_dev), _stream()), "eav_epoch_commit")
+
+    def _state(self):
+        c = self.core
+        return (c.params, c.grads, c.exp_avg, c.exp_avg_sq, c.bn_state, c.step_dev, self.epoch_dev, self.train_acc,
+                self.val_acc, self.history)
+
+    def capture(self, bn_train):
+        """Warm-up (really runs one epoch on a side stream), capture, roll every piece of state back."""
+        snap = [t.clone() for t in self._state()]
+        s = torch.cuda.Stream(device=self.core.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.enqueue(bn_train)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.enqueue(bn_train)
+        for t, v in zip(self._state(), snap):
+            t.copy_(v)
+        torch.cuda.synchronize()
+        self._graphs[bool(bn_train)] = g
+        return g
+
+    def run_epoch(self, bn_train, use_graph=True):
+        """Advance every model by one epoch (asynchronous: returns after the launch)."""
+        if not use_graph:
+            return self.enqueue(bn_train)
+        g = self._graphs.get(bool(bn_train))
+        if g is None:
+            g = self.capture(bn_train)
+        g.replay()
+
+    def epochs_done(self):
+        return int(self.epoch_dev.item())
+
+    def results(self):
+        """(history [epochs_done][M][3] CPU float32) -- one synchronisation."""
+        n = self.epochs_done()
+        return self.history[:min(n, self.max_epochs)].cpu()
+
+    @property
+    def samples_per_epoch(self):
+        return self.core.M * self.n_train

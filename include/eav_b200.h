@@ -239,6 +239,37 @@ int eav_adam_step_graph(float *params, const float *grads, float *exp_avg, float
 int eav_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_stride,
                     float maxnorm, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* Device-side epoch control: lets ONE CUDA graph hold a whole epoch of
+ * Trainer_uni.train() (CNN_torch/EEGNet_tor.py:96-116: the shuffled batches of
+ * DataLoader(shuffle=True), EEGNet_tor.py:92-93, incl. the ragged last batch) plus the
+ * validation pass (EEGNet_tor.py:118-135), with no host work between steps.       */
+/* ------------------------------------------------------------------------- */
+/*
+ * Fresh per-model permutation of the n_train training rows for the epoch *epoch_dev
+ * (Philox4x32-10 keyed by (seed; subject id, epoch, element); NOT torch's CPU mt19937 stream --
+ * parity runs keep the host DataLoader as the index source).
+ * sched    device i32 [ceil(n_train/batch)][n_models*batch]: step s starts at s*n_models*batch and
+ *          holds the x_index vector of eav_eegnet_forward for (n_models, B_s = min(batch, n_train - s*batch)),
+ *          model-major; entries are absolute rows first_row + m*rows_per_model + perm_m[.].
+ * subject_ids device i32 [n_models] or NULL (= 0..n_models-1): the random stream follows the subject,
+ *          not the slot, so results do not depend on how subjects are sharded over GPUs.
+ * epoch_dev device i64 epoch counter (read at run time; NULL = epoch 0).
+ */
+int eav_epoch_schedule(int32_t *sched, const int32_t *subject_ids, int32_t n_models, int32_t n_train,
+                       int32_t batch, int64_t rows_per_model, int64_t first_row, uint64_t seed,
+                       const int64_t *epoch_dev, void *stream);
+/* acc device f64 [n_models][2]: acc[m][0] += loss[m]; acc[m][1] += n_correct[m] (n_correct may be NULL).
+ * The running sums behind the per-epoch loss / accuracy the reference prints (EEGNet_tor.py:112-113,130-135). */
+int eav_epoch_accumulate(const float *loss, const int32_t *n_correct, int32_t n_models, double *acc,
+                         void *stream);
+/* End of epoch e = *epoch_dev: history[e % max_epochs][m] = {mean train loss over n_train_steps, mean validation
+ * loss over n_val_steps batches, validation accuracy = correct / n_val}; zeroes both accumulators; ++*epoch_dev.
+ * history device f32 [max_epochs][n_models][3]. */
+int eav_epoch_commit(double *train_acc, double *val_acc, int32_t n_models, int32_t n_train_steps,
+                     int32_t n_val_steps, int32_t n_val, float *history, int32_t max_epochs,
+                     int64_t *epoch_dev, void *stream);
+
 /* Measured-peak helper for bench.py: runs a register-resident FFMA loop on every SM
  * and returns the achieved fp32 TFLOP/s (host-synchronous; not part of the hot path). */
 int eav_measure_fp32_peak(double *tflops, void *stream);

@@ -3,9 +3,9 @@ mechanical shims SURVEY.md §0 F1-F3 documents, so its CPU path can be executed 
 this container to (a) pin the oracle restatement and (b) generate golden vectors.
 
 TEST INFRASTRUCTURE ONLY.  Nothing here is shipped, nothing is copied from the
-reference, and /root/reference does not exist on the GPU box: only
-oracle/gen_golden.py and the `-m "not gpu"` pin tests (skipped when the reference
-is absent) import this module.
+reference into the repository's history: only oracle/gen_golden.py, the `-m "not gpu"`
+pin tests (skipped when the reference is absent) and `bench.py --impl reference` (the
+CPU arm) import this module.
 
 Shims (all mechanical, none changes arithmetic):
   F1  CNN_torch/EEGNet_tor.py:4 imports `Fusion.VIT_audio.Transformer_audio`,
@@ -20,7 +20,11 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("EAV_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box (where it does not exist) the verbatim copy of the
+# path's four files that oracle/make_ref.py placed in the git-ignored oracle/_ref/.
+_LOCAL_REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REF_ROOT = os.environ.get("EAV_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/CNN_torch/EEGNet_tor.py") else _LOCAL_REF)
 
 
 def available() -> bool:
