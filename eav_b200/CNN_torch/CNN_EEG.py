@@ -12,7 +12,7 @@ from torch.utils.data import DataLoader, TensorDataset
 
 from ..ops import EegnetDims
 from .._lib import EAV_VARIANT_CNN
-from .._module_base import ArenaModule, FusedTrainerMixin
+from .._module_base import ArenaAdam, ArenaModule, FusedTrainerMixin
 
 
 class EEGNet(ArenaModule):
@@ -93,7 +93,7 @@ class EEGNetTrainer(FusedTrainerMixin):
         self.train_loader, self.test_loader = (DataLoader(ds, batch_size=batch_size, shuffle=sh)
                                                for ds, sh in ((train_dataset, True), (val_dataset, False)))
         self.criterion = nn.CrossEntropyLoss()
-        self.optimizer = optim.Adam(model.parameters(), lr=lr)
+        self.optimizer = ArenaAdam(model.parameters(), lr=lr)       # optim.Adam whose state is the fused trainer's
         trx, try_ = _dataset_tensors(train_dataset)
         tex, tey = _dataset_tensors(val_dataset)
         self._setup_fused(self.model, trx, try_, tex, tey, lr=lr, batch_size=batch_size)

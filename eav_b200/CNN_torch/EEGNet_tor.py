@@ -20,7 +20,7 @@ from torch.utils.data import DataLoader, TensorDataset
 from .. import _lib
 from ..ops import EegnetDims, EegnetEngine
 from .._lib import EAV_VARIANT_TOR
-from .._module_base import ArenaModule, FusedTrainerMixin
+from .._module_base import ArenaAdam, ArenaModule, FusedTrainerMixin
 
 
 class EEGNet_tor(ArenaModule):
@@ -53,7 +53,7 @@ class EEGNet_tor(ArenaModule):
             setattr(self, name, ctor())
         self._dims = EegnetDims(nb_classes, Chans=Chans, Samples=Samples, dropoutRate=dropoutRate,
                                 kernLength=kernLength, F1=F1, D=D, F2=F2, norm_rate=norm_rate,
-                                variant=EAV_VARIANT_TOR)
+                                variant=EAV_VARIANT_TOR, dropout2d=dropoutType != 'Dropout')
         self._dropout2d = dropoutType != 'Dropout'
         self._param_modules = ("firstConv.weight", "firstBN.weight", "firstBN.bias", "depthwiseConv.weight",
                                "depthwiseBN.weight", "depthwiseBN.bias", "separableConv.weight",
@@ -77,7 +77,7 @@ class Trainer_uni(FusedTrainerMixin):
         self.test_dataloader = self._prepare_dataloader(self.te_x, self.te_y, shuffle=False)
         self.model = model
         self.criterion = nn.CrossEntropyLoss()
-        self.optimizer = optim.Adam(model.parameters(), lr=lr)
+        self.optimizer = ArenaAdam(model.parameters(), lr=lr)       # optim.Adam whose state is the fused trainer's
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(device)

@@ -96,7 +96,11 @@ class DataLoadEEG:
 
     def _raw_device(self, seg):
         """(Channels, Time, Trials) host array -> device tensor [1][trials][ch][time] (the .mat memory order)."""
-        if seg is self.seg and self._raw_trial_major is not None:
+        # the cached trial-major view is only trusted while self.seg still IS a view of it (a caller may have
+        # re-assigned loader.seg after load_mat_data())
+        if (seg is self.seg and self._raw_trial_major is not None and isinstance(seg, np.ndarray)
+                and seg.shape == tuple(np.transpose(self._raw_trial_major, (1, 2, 0)).shape)
+                and np.shares_memory(seg, self._raw_trial_major)):
             arr = np.ascontiguousarray(self._raw_trial_major)          # already in the kernels' layout
         else:
             arr = np.ascontiguousarray(np.transpose(np.asarray(seg), (2, 0, 1)))

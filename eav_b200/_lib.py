@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libeav_b200.so")
 
 EAV_VARIANT_TOR, EAV_VARIANT_CNN = 0, 1
-EAV_DROPOUT_NONE, EAV_DROPOUT_MASK, EAV_DROPOUT_PHILOX = 0, 1, 2
+EAV_DROPOUT_NONE, EAV_DROPOUT_MASK, EAV_DROPOUT_PHILOX, EAV_DROPOUT_PHILOX_2D = 0, 1, 2, 3
 
 
 class PreprocCfg(Structure):

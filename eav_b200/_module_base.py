@@ -61,6 +61,18 @@ class ArenaModule(nn.Module):
         self._fwd_id = 0
         self._philox_step = 0
 
+    # ------------------------------------------------------------ copy / pickle
+    def __getstate__(self):
+        """copy.deepcopy(model) (best-model snapshots), torch.save(model) and pickling work after a forward like for
+        the reference nn.Module: the engines (ctypes handles, workspaces) and the arena handles are not part of the
+        state -- the copy's parameters stay views of ONE copied storage and _ensure_arena() re-adopts or repacks them
+        on its next forward."""
+        st = self.__dict__.copy()
+        st["_engines"] = {}
+        st["_arena"] = None
+        st["_bn_arena"] = None
+        return st
+
     # ------------------------------------------------------------ arena management
     def _named_param_list(self):
         mods = dict(self.named_parameters())
@@ -163,7 +175,7 @@ class ArenaModule(nn.Module):
         if self.training:
             self._bump_bn_counters()
             if d.dropoutRate > 0:
-                if self.dropout_source == "torch_cpu" or self._dropout2d:
+                if self.dropout_source == "torch_cpu":
                     masks = self._draw_masks(B, x3.device)
                 else:
                     self._philox_step += 1
@@ -176,6 +188,62 @@ class ArenaModule(nn.Module):
         eng._owner_fwd_id = self._fwd_id
         return eng.forward(x3, self._arena, self._bn_arena, bn_train=self.training,
                            mask1=masks[0] if masks else None, mask2=masks[1] if masks else None, philox=philox)
+
+
+class ArenaAdam(torch.optim.Adam):
+    """torch.optim.Adam (EEGNet_tor.py:82, CNN_EEG.py:86) whose per-parameter state IS the fused trainer's state:
+    `exp_avg` / `exp_avg_sq` are views of the trainer's flat moment arenas and `step` mirrors its device-side
+    step counter, so `trainer.optimizer.state_dict()` checkpoints the real Adam moments, `load_state_dict()`
+    resumes them, and an edited `param_groups[0]['lr']` (LR schedulers) is what the next fused step uses."""
+
+    def bind(self, core, layout, plist):
+        self._core, self._layout, self._plist = core, layout, list(plist)
+        self._alias()
+        return self
+
+    def _alias(self):
+        c = self._core
+        t = float(c.step_dev.item())
+        for p, (name, off, shape) in zip(self._plist, self._layout):
+            n = int(np.prod(shape))
+            st = self.state[p]
+            st["step"] = torch.tensor(t, dtype=torch.float32)
+            st["exp_avg"] = c.exp_avg[0, off:off + n].view(shape)
+            st["exp_avg_sq"] = c.exp_avg_sq[0, off:off + n].view(shape)
+
+    def state_dict(self):
+        if getattr(self, "_core", None) is not None:
+            t = float(self._core.step_dev.item())
+            for p in self._plist:
+                self.state[p]["step"].fill_(t)
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        c = getattr(self, "_core", None)
+        if c is None:
+            return
+        steps = set()
+        for p, (name, off, shape) in zip(self._plist, self._layout):
+            st, n = self.state.get(p, {}), int(np.prod(shape))
+            if "exp_avg" in st:
+                c.exp_avg[0, off:off + n].copy_(st["exp_avg"].reshape(-1))
+                c.exp_avg_sq[0, off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("eav_b200: the fused Adam keeps ONE step count for all parameters")
+        if steps:
+            c.step_dev.fill_(steps.pop())
+        c.set_lr(float(self.param_groups[0]["lr"]))
+        self._alias()
+
+    def step(self, closure=None):
+        """A manual optimizer.step() (p.grad populated by loss.backward() through the autograd Function) updates the
+        same arenas the fused steps use; the shared step count advances with it."""
+        out = super().step(closure)
+        if getattr(self, "_core", None) is not None:
+            self._core.step_dev += 1
+        return out
 
 
 def _as_rows(x, chans, samples):
@@ -211,6 +279,9 @@ class FusedTrainerMixin:
         self._core = SubjectBatchTrainer(d, 1, x_all, y_all, lr=lr if lr is not None else self.lr, max_batch=bs,
                                          params=model._arena, bn_state=model._bn_arena,
                                          seed=torch.initial_seed() & (2 ** 63 - 1))
+        opt = getattr(self, "optimizer", None)
+        if isinstance(opt, ArenaAdam):
+            opt.bind(self._core, model._layout, model._named_param_list())
 
     def _index_batches(self, train=True):
         loader = self._train_index_loader if train else self._test_index_loader
@@ -224,10 +295,13 @@ class FusedTrainerMixin:
         if not model._arena_ok():
             raise RuntimeError("eav_b200: model parameters were re-allocated after the trainer was built "
                                "(e.g. model.to(...)); rebuild the trainer")
+        opt = getattr(self, "optimizer", None)
+        if opt is not None and opt.param_groups and float(opt.param_groups[0]["lr"]) != self._core.lr:
+            self._core.set_lr(float(opt.param_groups[0]["lr"]))       # LR scheduler / manual edit of param_groups
         masks = None
         if model.training:
             model._bump_bn_counters()
-            if model._dims.dropoutRate > 0 and (model.dropout_source == "torch_cpu" or model._dropout2d):
+            if model._dims.dropoutRate > 0 and model.dropout_source == "torch_cpu":
                 masks = model._draw_masks(rows.numel(), self._core.device)
         loss = self._core.train_step(rows, bn_train=model.training, masks=masks)
         if getattr(self, "record_losses", False):      # test / logging hook: keeps a device copy, no sync

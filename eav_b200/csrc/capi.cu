@@ -18,6 +18,23 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < 64 ? dev : 63;
+}
+
+int device_sm_count() {
+    static PerDevice<int> sms(0);
+    int &n = sms.here();
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 int make_dims(const eav_eegnet_cfg *c, NetDims *d) {
     EAV_REQUIRE(c != nullptr, EAV_ERR_BAD_ARG, "cfg is NULL");
     EAV_REQUIRE(c->n_models > 0 && c->batch > 0, EAV_ERR_BAD_ARG, "n_models=%d batch=%d must be positive", c->n_models, c->batch);
@@ -25,7 +42,7 @@ int make_dims(const eav_eegnet_cfg *c, NetDims *d) {
                     c->kern_len2 > 0 && c->pool1 > 0 && c->pool2 > 0 && c->n_classes > 0,
                 EAV_ERR_BAD_ARG, "all model dimensions must be positive");
     EAV_REQUIRE(c->variant == EAV_VARIANT_TOR || c->variant == EAV_VARIANT_CNN, EAV_ERR_BAD_ARG, "unknown variant %d", c->variant);
-    EAV_REQUIRE(c->dropout_mode >= 0 && c->dropout_mode <= 2, EAV_ERR_BAD_ARG, "unknown dropout_mode %d", c->dropout_mode);
+    EAV_REQUIRE(c->dropout_mode >= 0 && c->dropout_mode <= 3, EAV_ERR_BAD_ARG, "unknown dropout_mode %d", c->dropout_mode);
     EAV_REQUIRE(c->dropout_p >= 0.f && c->dropout_p <= 1.f, EAV_ERR_BAD_ARG, "dropout_p=%f out of [0,1]", c->dropout_p);
     EAV_REQUIRE((int64_t)c->n_models * c->batch < (1ll << 24), EAV_ERR_UNSUPPORTED, "n_models*batch too large");
     d->M = c->n_models; d->B = c->batch; d->N = d->M * d->B;

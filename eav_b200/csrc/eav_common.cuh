@@ -28,6 +28,18 @@ void count_launch();   // bumps the process-wide kernel-launch counter (eav_laun
         }                                                                         \
     } while (0)
 
+// One slot per CUDA device for launcher-side caches.  cudaFuncSetAttribute (opt-in dynamic shared memory) and
+// the SM count are properties of a DEVICE, so a process-wide `static bool attr_set` would leave the second GPU
+// of a single process ("one process, 8 streams") without its > 48 KB opt-in.
+int current_device_slot();     // cudaGetDevice() clamped to [0, 64)
+int device_sm_count();         // multiprocessor count of the current device (cached per device)
+template <typename T>
+struct PerDevice {
+    T v[64];
+    explicit PerDevice(T init) { for (int i = 0; i < 64; ++i) v[i] = init; }
+    T &here() { return v[current_device_slot()]; }
+};
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -51,6 +51,7 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
         int64_t e = (int64_t)n * FEAT + i;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask2[e] ? s * inv_keep : 0.f;
         else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 2u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) s = philox_keep(seed, step, 18u, (uint64_t)((int64_t)n * F2 + i / T32), p_drop) ? s * inv_keep : 0.f;
         dfeat_s[i] = s * (1.f / (float)P2);
     }
     __syncthreads();
@@ -355,7 +356,8 @@ int launch_sepconv_bwd_dw(const NetDims &d, const float *dz3, const float *y3, c
     if (sepconv_use_tc(d))      // tcgen05 path (sepconv_tc.cu); dz3 already holds dy3 (bn_bwd_apply stage)
         return launch_sepconv_dw_tc(d, dz3, d1, part, grads, splits, st);
     size_t smem = (size_t)2 * (d.F2 * SW_UP + SW_GC * SW_XS) * sizeof(float);
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(sepconv_bwd_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
@@ -435,7 +437,8 @@ int launch_pw_bwd(const NetDims &d, const float *dz3, const float *y3, const flo
                   float *grads, cudaStream_t st) {
     size_t smem = (size_t)(d.F2 * d.T4 + d.F2 * d.G) * sizeof(float);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "pw_bwd: F2*T4 too large");
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(pw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
@@ -506,6 +509,7 @@ pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, co
         bool keep = true;
         if (dropout_mode == EAV_DROPOUT_MASK) keep = mask1[e] != 0;
         else if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep(seed, step, 1u, (uint64_t)e, p_drop);
+        else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) keep = philox_keep(seed, step, 17u, (uint64_t)row, p_drop);
         return keep ? dd1[e] * sc : 0.f;
     };
     if (P1 == 4 && (T & 3) == 0) {              // one pooling window == one aligned float4
@@ -525,6 +529,7 @@ pool1_bwd_kernel(const float *__restrict__ dd1, const float *__restrict__ y2, co
             }
             uint32_t keep = 0xFu;
             if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep4(seed, step, 1u, (uint64_t)(eb >> 2), p_drop);
+            else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) keep = philox_keep(seed, step, 17u, (uint64_t)row, p_drop) ? 0xFu : 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t u = eb + j - e0;
@@ -781,7 +786,8 @@ int launch_dw_bwd(const NetDims &d, const float *dz2, const float *y2, const flo
     size_t fl = (size_t)d.C * TSa + (size_t)8 * TSa + 8 * d.C + redn;
     size_t smem = fl * sizeof(float);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "dw_bwd: Chans*Samples too large for one CTA");
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(dw_bwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(dw_bwd_kernel<30, 500, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -993,7 +999,8 @@ static int launch_tconv_bwd_dw_rk(const NetDims &d, const float *x, const int32_
                                   cudaStream_t st, int cpm) {
     size_t smem = tconv_dw_smem<RK>(d.T);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_bwd_dw: Samples=%d too large", d.T);
-    static bool attr_set = false;   // one flag per RK instantiation
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();   // one flag per RK instantiation
     if (!attr_set) {
         cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(tconv_bwd_dw_kernel<8, RK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

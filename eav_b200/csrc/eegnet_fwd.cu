@@ -203,8 +203,10 @@ static int launch_tconv_fwd_v(const NetDims &d, const float *x, const int32_t *x
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "tconv_fwd: kernLength %d too large", d.K1);
     const int groups = cdiv(d.C, ROWS), tiles = cdiv(d.T, TC_TT);
     const int64_t n_items = (int64_t)d.N * groups * tiles;
-    static int resident = 0;          // CTAs the device holds at once (SMs x occupancy)
-    static size_t resident_smem = 0;
+    static PerDevice<int> resident_pd(0);          // CTAs the device holds at once (SMs x occupancy)
+    static PerDevice<size_t> resident_smem_pd(0);
+    int &resident = resident_pd.here();
+    size_t &resident_smem = resident_smem_pd.here();
     if (resident == 0 || resident_smem != smem) {
         cudaFuncSetAttribute(tconv_fwd_kernel<8, ROWS, KU, MINB, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int dev = 0, sms = 148, per_sm = 1;
@@ -487,6 +489,7 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
             }
             uint32_t keep = 0xFu;
             if (dropout_mode == EAV_DROPOUT_PHILOX) keep = philox_keep4(seed, step, 1u, (uint64_t)(eb >> 2), p_drop);
+            else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) keep = philox_keep(seed, step, 17u, (uint64_t)row, p_drop) ? 0xFu : 0u;
             float o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -494,7 +497,7 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
                 float sj = (elu_f(fmaf(v[j].x, st.z, st.w)) + elu_f(fmaf(v[j].y, st.z, st.w)) +
                             elu_f(fmaf(v[j].z, st.z, st.w)) + elu_f(fmaf(v[j].w, st.z, st.w))) * invp;
                 if (dropout_mode == EAV_DROPOUT_MASK) sj = (u >= 0 && u < T4 && mask1[eb + j]) ? sj * inv_keep : 0.f;
-                else if (dropout_mode == EAV_DROPOUT_PHILOX) sj = ((keep >> j) & 1u) ? sj * inv_keep : 0.f;
+                else if (dropout_mode >= EAV_DROPOUT_PHILOX) sj = ((keep >> j) & 1u) ? sj * inv_keep : 0.f;
                 o[j] = sj;
             }
             if (eb >= e0 && eb + 3 < e0 + T4) {
@@ -514,6 +517,7 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
         const int64_t e = row * T4 + u;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[e] ? s * inv_keep : 0.f;
         else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 1u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) s = philox_keep(seed, step, 17u, (uint64_t)row, p_drop) ? s * inv_keep : 0.f;
         d1[e] = s;
     }
 }
@@ -762,7 +766,8 @@ int launch_sepconv_fwd(const NetDims &d, const float *d1, const float *params, f
     EAV_REQUIRE(d.K2 == SC_K, EAV_ERR_UNSUPPORTED, "sepconv: kernel length %d unsupported (only 16)", d.K2);
     size_t smem = sepconv_smem(d.G);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv: F1*D=%d too large", d.G);
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(sepconv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
@@ -783,7 +788,8 @@ int launch_sepconv_bwd_dx(const NetDims &d, const float *dz3, const float *y3, c
     if (sepconv_use_tc(d)) return launch_sepconv_tc(d, 1, dz3, params, wt_scratch, dd1, nullptr, nullptr, st);
     size_t smem = sepconv_smem(d.F2);
     EAV_REQUIRE(smem <= 200 * 1024, EAV_ERR_UNSUPPORTED, "sepconv_dx: F2=%d too large", d.F2);
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(sepconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
@@ -897,6 +903,7 @@ tail_fwd_kernel(const float *__restrict__ y3, const float4 *__restrict__ bn3,
         int64_t e = (int64_t)n * FEAT + i;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask2[e] ? s * inv_keep : 0.f;
         else if (dropout_mode == EAV_DROPOUT_PHILOX) s = philox_keep(seed, step, 2u, (uint64_t)e, p_drop) ? s * inv_keep : 0.f;
+        else if (dropout_mode == EAV_DROPOUT_PHILOX_2D) s = philox_keep(seed, step, 18u, (uint64_t)((int64_t)n * F2 + o), p_drop) ? s * inv_keep : 0.f;
         feat_s[i] = s;
         feat[e] = s;
     }

@@ -7,11 +7,15 @@
 // table of peer base pointers):   [slot 0 | slot 1 | flags[PR_MAX_CTAS][PR_MAX_WORLD]].
 //   1. CTA c copies its chunk of the local source into slot (call & 1) of the OWN exchange buffer,
 //   2. publishes flags[c][rank] = call in every peer's buffer (system-scope release) and waits until all peers'
-//      CTA c have published the same call number (bounded spin, then __trap),
+//      CTA c have published the same call number (spin bounded by wall time, then __trap),
 //   3. sums chunk c of every rank's slot in RANK ORDER (every rank computes bit-identical results) into dst.
 // Two slots make a trailing barrier unnecessary: a rank can be at most one call ahead of a peer that still reads.
 #include "eav_common.cuh"
 #include "../../include/eav_b200.h"
+
+#ifndef EAV_PEER_TIMEOUT_NS
+#define EAV_PEER_TIMEOUT_NS 120000000000ull
+#endif
 
 namespace eav {
 namespace {
@@ -40,9 +44,17 @@ peer_allreduce_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t n,
         volatile uint32_t *theirs = reinterpret_cast<volatile uint32_t *>(base[tid] + flags_off) + rank;
         *theirs = call;                                           // tell rank `tid` that my chunk `cta` is in place
         volatile uint32_t *ours = reinterpret_cast<volatile uint32_t *>(base[rank] + flags_off) + tid;
+        // A late peer (first-step module load, a host stall between eager steps, checkpoint I/O) is waited for, as
+        // NCCL would: the bound is wall time (EAV_PEER_TIMEOUT_NS, default 120 s), only a rank that never arrives traps.
         uint32_t spins = 0;
+        unsigned long long t0 = 0;
         while ((int32_t)(*ours - call) < 0) {                      // wrap-safe "flag >= call"
-            if (++spins > (1u << 24)) __trap();
+            if ((++spins & 0xFFFFu) == 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > EAV_PEER_TIMEOUT_NS) __trap();
+            }
         }
         __threadfence_system();
     }

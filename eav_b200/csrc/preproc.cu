@@ -609,7 +609,8 @@ static int launch_fir_5_101(const eav_preproc_cfg *c, const TIn *raw, const FirT
     if (sizeof(TIn) == 4 && tile_out == chunk && (tile_out % FIR_R) == 0 && (c->trial_len & 3) == 0 &&
         (reinterpret_cast<uintptr_t>(raw) & 15) == 0 && c->trial_len >= 64)
         use_tma = 1;
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaFuncSetAttribute(fir_decimate_kernel<TIn, 5, 101, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;

@@ -522,18 +522,14 @@ int launch_sepconv_tc(const NetDims &d, int mode, const float *in, const float *
     if (mode == 0) sepconv_wt_pack_kernel<0><<<dim3(8, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
     else sepconv_wt_pack_kernel<1><<<dim3(8, d.M), 256, 0, st>>>(params, d.pstride, d.oW3, wt);
     EAV_CUDA_LAUNCH_CHECK("sepconv_wt_pack");
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(sepconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCT_SMEM);
         EAV_REQUIRE(e == cudaSuccess, (int)e, "sepconv_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sm_count();
     const int n_pairs = d.M * ((d.B + 1) / 2);
     const int grid = n_pairs < sms ? n_pairs : sms;
     const int PL = mode == 0 ? d.pad2l : d.K2 - 1 - d.pad2l;
@@ -559,18 +555,14 @@ int sepconv_dw_tc_splits(const NetDims &d) {
 
 int launch_sepconv_dw_tc(const NetDims &d, const float *dy3, const float *d1, float *part, float *grads, int S,
                          cudaStream_t st) {
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(sepconv_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SDW_SMEM);
         EAV_REQUIRE(e == cudaSuccess, (int)e, "sepconv_dw_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sm_count();
     const int units = d.M * S;
     sepconv_dw_tc_kernel<<<units < sms ? units : sms, SDW_THREADS, SDW_SMEM, st>>>(dy3, d1, part, d.M, d.B, d.T4,
                                                                                    d.pad2l, S);

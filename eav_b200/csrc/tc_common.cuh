@@ -54,11 +54,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.  The bound is
+// WALL TIME (%globaltimer), not a poll count: a poll count fires spuriously whenever the waiting CTA is merely slow
+// -- under compute-sanitizer, a debugger, MPS time-slicing or a pre-empted context -- and a trap kills the
+// training context.  EAV_SPIN_TIMEOUT_NS (build flag) defaults to 20 s; the clock is read once per 2^14 polls.
+#ifndef EAV_SPIN_TIMEOUT_NS
+#define EAV_SPIN_TIMEOUT_NS 20000000000ull
+#endif
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+    unsigned long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if ((++spins & 0x3FFFu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > EAV_SPIN_TIMEOUT_NS) __trap();
+        }
     }
 }
 

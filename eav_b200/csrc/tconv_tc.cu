@@ -335,18 +335,14 @@ int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index
     tconv_wt_pack_kernel<<<dim3(ksteps, d.M), 512, 0, st>>>(params, d.pstride, d.oW1, d.K1, ksteps, wt_scratch);
     EAV_CUDA_LAUNCH_CHECK("tconv_wt_pack");
     const size_t smem = ((size_t)ksteps * TCF_WROW + (size_t)TCF_STAGES * 2 * xs_len) * 4;
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tconv_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
         EAV_REQUIRE(e == cudaSuccess, (int)e, "tconv_fwd_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sm_count();
     const int n_rows = d.N * d.C;
     int grid = 2 * sms;
     if (grid > n_rows) grid = n_rows;
@@ -634,18 +630,14 @@ int launch_tconv_bwd_dw_tc(const NetDims &d, const float *x, const int32_t *x_in
                            const float *y1, const float4 *bnf1, const float4 *bnb1, float *part, int S,
                            cudaStream_t st) {
     const size_t smem = ((size_t)TCW_STAGES * TCW_STAGE_FLOATS + 384 * TCW_SP) * 4;
-    static bool attr_set = false;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tconv_bwd_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         EAV_REQUIRE(e == cudaSuccess, (int)e, "tconv_bwd_dw_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sm_count();
     const int units = 2 * d.M * S;
     const int grid = units < sms ? units : sms;
     tconv_bwd_dw_tc_kernel<<<grid, TCW_THREADS, smem, st>>>(x, x_index, dz1, y1, bnf1, bnb1, d.bn_train, d.M, d.B, d.C,

@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from . import _lib
 from ._lib import EAV_DROPOUT_MASK, EAV_DROPOUT_NONE, EAV_DROPOUT_PHILOX
-from .ops import EegnetDims, _ptr, _stream
+from .ops import EegnetDims, _on, _ptr, _stream
 
 
 class PeerExchange:
@@ -54,9 +54,10 @@ class PeerExchange:
         if call is None:
             self.call += 1
             call = self.call & 0xFFFFFFFF or 1
-        _lib.check(self.lib.eav_peer_allreduce(_ptr(t), _ptr(t), t.numel(), int(t.dtype == torch.float64),
-                                               _ptr(self.bases), self.world, self.rank, self.slot_bytes, int(call),
-                                               _ptr(call_base), int(calls_per_step), _stream()), "eav_peer_allreduce")
+        with _on(t.device):
+            _lib.check(self.lib.eav_peer_allreduce(_ptr(t), _ptr(t), t.numel(), int(t.dtype == torch.float64),
+                                                   _ptr(self.bases), self.world, self.rank, self.slot_bytes, int(call),
+                                                   _ptr(call_base), int(calls_per_step), _stream()), "eav_peer_allreduce")
         return t
 
 
@@ -176,6 +177,10 @@ class DataParallelEEGNet:
             self.step_dev += 1
 
     def step(self, x, y, bn_train=True, masks=None, update=True, graph=False):
+        with _on(self.device):
+            return self._step(x, y, bn_train, masks, update, graph)
+
+    def _step(self, x, y, bn_train=True, masks=None, update=True, graph=False):
         """x [B_local][Chans][Samples] f32, y [B_local] i64 (this rank's slice of the global batch).
         Returns the GLOBAL mean loss (device scalar).  masks: optional explicit dropout keep-masks
         for this rank's samples (parity tests); otherwise on-device Philox.
@@ -183,7 +188,7 @@ class DataParallelEEGNet:
         it needs the "peer" collective (or a single rank) and on-device dropout."""
         d = self.dims
         drop = bn_train and d.dropoutRate > 0
-        mode = EAV_DROPOUT_NONE if not drop else (EAV_DROPOUT_MASK if masks is not None else EAV_DROPOUT_PHILOX)
+        mode = EAV_DROPOUT_NONE if not drop else (EAV_DROPOUT_MASK if masks is not None else d.philox_mode)
         m1, m2 = masks if masks is not None else (None, None)
         self.t += 1
         if not graph:

@@ -59,6 +59,10 @@ def _parse_matrix(buf, off, nbytes, end):
     t, n, d, off = _tag(buf, off, end)             # real part
     if t not in _MI:
         return name, dims, None, 0, 0
+    # MATLAB may store a class-double array in a narrower element type ("numeric data compression").  The reference
+    # calls scipy.io.loadmat with its defaults (Dataload_eeg.py:70,77; mat_dtype=False), which returns the STORAGE
+    # dtype in that case -- so does this reader (pinned by tests/test_mat_ingest_cpu.py against loadmat itself);
+    # DataLoadEEG widens non-float recordings to float64 before they reach the kernels, as scipy's filters would.
     return name, dims, np.dtype(end + _MI[t]), d, n
 
 
@@ -80,8 +84,8 @@ def read_mat_array(path, names):
             if info and info[0] in names and info[2] is not None:
                 name, dims, dt, po, pn = info
                 count = int(np.prod(dims))
-                if pn < count * dt.itemsize:       # stored in a narrower integer type: let scipy widen it
-                    raise MatFormatError("payload narrower than the array class")
+                if pn < count * dt.itemsize:
+                    raise MatFormatError("truncated payload")
                 arr = np.memmap(path, dtype=dt, mode="r", offset=po, shape=tuple(reversed(dims)))
                 return arr, name, True
         elif t == _MI_COMPRESSED:
@@ -99,7 +103,7 @@ def read_mat_array(path, names):
                     raw = zlib.decompress(bytes(mm[d:d + n]))
                     count = int(np.prod(dims))
                     if pn < count * dt.itemsize:
-                        raise MatFormatError("payload narrower than the array class")
+                        raise MatFormatError("truncated payload")
                     arr = np.frombuffer(raw, dtype=dt, count=count, offset=po).reshape(tuple(reversed(dims)))
                     return arr, name, False
         off = nxt

@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (EAV_DROPOUT_MASK, EAV_DROPOUT_NONE, EAV_DROPOUT_PHILOX, EAV_VARIANT_CNN, EAV_VARIANT_TOR,
+from ._lib import (EAV_DROPOUT_MASK, EAV_DROPOUT_NONE, EAV_DROPOUT_PHILOX, EAV_DROPOUT_PHILOX_2D, EAV_VARIANT_CNN,
+                   EAV_VARIANT_TOR,
                    EegnetCfg, PreprocCfg)
 
 TOR_PARAM_NAMES = ("firstConv.weight", "firstBN.weight", "firstBN.bias", "depthwiseConv.weight",
@@ -26,14 +27,25 @@ def _ptr(t):
 
 
 def _stream():
+    """The CURRENT device's current stream.  The C ABI launches on the current device (kernel attributes, SM count
+    and the launch itself are per device), so every caller first makes the device that owns its tensors current
+    (`with _on(device):`) -- a Trainer_uni(device='cuda:1') in a process whose current device is 0 then launches
+    on GPU 1's stream with GPU 1's pointers."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _chk_cuda(t, dtype, name):
+def _on(device):
+    """Context manager: `device` is the current CUDA device inside the block."""
+    return torch.cuda.device(device)
+
+
+def _chk_cuda(t, dtype, name, device=None):
     if t is None:
         return
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (eav_b200 has no CPU path)")
+    if device is not None and t.device != device:
+        raise RuntimeError(f"{name} lives on {t.device}, the engine on {device}")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -58,6 +70,12 @@ class EegnetDims:
     pool2: int = 8
     bn_eps: float = 1e-5
     bn_momentum: float = 0.1
+    dropout2d: bool = False     # dropoutType != 'Dropout' (EEGNet_tor.py:21): nn.Dropout2d, whole channels dropped
+
+    @property
+    def philox_mode(self):
+        """The on-device dropout mode of this model (element-wise or per (sample, channel) row)."""
+        return EAV_DROPOUT_PHILOX_2D if self.dropout2d else EAV_DROPOUT_PHILOX
 
     @property
     def n_bn(self):
@@ -150,16 +168,17 @@ class EegnetEngine:
     def forward(self, x, params, bn_state, bn_train=False, x_index=None, mask1=None, mask2=None, philox=None,
                 out=None):
         """x [rows][C][T] f32; params [M][P]; bn_state [M][n_bn]; returns out [M*B][nb_classes]."""
-        _chk_cuda(x, torch.float32, "x"); _chk_cuda(params, torch.float32, "params")
-        _chk_cuda(bn_state, torch.float32, "bn_state"); _chk_cuda(x_index, torch.int32, "x_index")
-        _chk_cuda(mask1, torch.uint8, "mask1"); _chk_cuda(mask2, torch.uint8, "mask2")
+        dv = self.device
+        _chk_cuda(x, torch.float32, "x", dv); _chk_cuda(params, torch.float32, "params", dv)
+        _chk_cuda(bn_state, torch.float32, "bn_state", dv); _chk_cuda(x_index, torch.int32, "x_index", dv)
+        _chk_cuda(mask1, torch.uint8, "mask1", dv); _chk_cuda(mask2, torch.uint8, "mask2", dv)
         mode = EAV_DROPOUT_NONE
         seed = step = 0
         if bn_train and self.dims.dropoutRate > 0:
             if mask1 is not None:
                 mode = EAV_DROPOUT_MASK
             elif philox is not None:
-                mode, (seed, step) = EAV_DROPOUT_PHILOX, philox
+                mode, (seed, step) = self.dims.philox_mode, philox
             else:
                 raise ValueError("train-mode forward needs dropout masks or a philox (seed, step)")
         n = self.M * self.B
@@ -169,47 +188,52 @@ class EegnetEngine:
             out = torch.empty(n, self.dims.nb_classes, dtype=torch.float32, device=self.device)
         c = self._cfg(params, bn_state, bn_train, mode, seed, step)
         self._last = (c, mode)
-        _lib.check(self.lib.eav_eegnet_forward(ctypes.byref(c), _ptr(x), _ptr(x_index), _ptr(params), _ptr(bn_state),
-                                               _ptr(mask1), _ptr(mask2), _ptr(out), _ptr(self.workspace),
-                                               self.ws_bytes, _stream()), "eav_eegnet_forward")
+        with _on(self.device):
+            _lib.check(self.lib.eav_eegnet_forward(ctypes.byref(c), _ptr(x), _ptr(x_index), _ptr(params), _ptr(bn_state),
+                                                   _ptr(mask1), _ptr(mask2), _ptr(out), _ptr(self.workspace),
+                                                   self.ws_bytes, _stream()), "eav_eegnet_forward")
         return out
 
     def loss(self, out, targets, x_index=None, want_grad=True):
-        _chk_cuda(out, torch.float32, "out"); _chk_cuda(targets, torch.int64, "targets")
+        _chk_cuda(out, torch.float32, "out", self.device); _chk_cuda(targets, torch.int64, "targets", self.device)
         loss = torch.empty(self.M, dtype=torch.float32, device=self.device)
         ncorrect = torch.empty(self.M, dtype=torch.int32, device=self.device)
         dout = torch.empty_like(out) if want_grad else None
         c = self.dims.cfg(self.M, self.B)
-        _lib.check(self.lib.eav_eegnet_loss(ctypes.byref(c), _ptr(out), _ptr(targets), _ptr(x_index), _ptr(loss),
-                                            _ptr(dout), _ptr(ncorrect), _stream()), "eav_eegnet_loss")
+        with _on(self.device):
+            _lib.check(self.lib.eav_eegnet_loss(ctypes.byref(c), _ptr(out), _ptr(targets), _ptr(x_index), _ptr(loss),
+                                                _ptr(dout), _ptr(ncorrect), _stream()), "eav_eegnet_loss")
         return loss, dout, ncorrect
 
     def backward(self, x, params, dout, grads=None, x_index=None, mask1=None, mask2=None):
         """Gradient of the LAST forward() (same cfg / workspace). Returns grads [M][P]."""
         c, _ = self._last
-        _chk_cuda(dout, torch.float32, "dout")
+        _chk_cuda(dout, torch.float32, "dout", self.device)
         if grads is None:
             grads = torch.zeros(self.M, params.stride(0) if params.dim() == 2 else self.n_params,
                                 dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.eav_eegnet_backward(ctypes.byref(c), _ptr(x), _ptr(x_index), _ptr(params), _ptr(dout),
-                                                _ptr(mask1), _ptr(mask2), _ptr(grads), _ptr(self.workspace),
-                                                self.ws_bytes, _stream()), "eav_eegnet_backward")
+        with _on(self.device):
+            _lib.check(self.lib.eav_eegnet_backward(ctypes.byref(c), _ptr(x), _ptr(x_index), _ptr(params), _ptr(dout),
+                                                    _ptr(mask1), _ptr(mask2), _ptr(grads), _ptr(self.workspace),
+                                                    self.ws_bytes, _stream()), "eav_eegnet_backward")
         return grads
 
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8):
     for t, nm in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _chk_cuda(t, torch.float32, nm)
-    _lib.check(_lib.load().eav_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
-                                         int(step), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                                         _stream()), "eav_adam_step")
+    with _on(params.device):
+        _lib.check(_lib.load().eav_adam_step(_ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), params.numel(),
+                                             int(step), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                             _stream()), "eav_adam_step")
 
 
 def renorm_rows(w2d, maxnorm):
     _chk_cuda(w2d, torch.float32, "w")
     rows, ln = w2d.shape
-    _lib.check(_lib.load().eav_renorm_rows(_ptr(w2d), rows, ln, w2d.stride(0), float(maxnorm), _stream()),
-               "eav_renorm_rows")
+    with _on(w2d.device):
+        _lib.check(_lib.load().eav_renorm_rows(_ptr(w2d), rows, ln, w2d.stride(0), float(maxnorm), _stream()),
+                   "eav_renorm_rows")
 
 
 def measure_fp32_peak(mode=0) -> float:
@@ -268,7 +292,7 @@ class PreprocEngine:
         epoch_slot i32 [S][trials] (device).  Returns epochs [S][n_epochs_out][ch][ep_len] f32
         (and dec [S][ch][n_dec] f32 when want_dec)."""
         c = self.cfg
-        _chk_cuda(raw, self.raw_dtype, "raw"); _chk_cuda(epoch_slot, torch.int32, "epoch_slot")
+        _chk_cuda(raw, self.raw_dtype, "raw", self.device); _chk_cuda(epoch_slot, torch.int32, "epoch_slot", self.device)
         if tuple(raw.shape) != (c.n_subjects, c.n_trials, c.n_chans, c.trial_len):
             raise ValueError(f"raw has shape {tuple(raw.shape)}")
         taps = np.ascontiguousarray(taps, dtype=np.float64)
@@ -280,7 +304,8 @@ class PreprocEngine:
                                  device=self.device)
         dec = torch.empty(c.n_subjects, c.n_chans, self.n_dec, dtype=torch.float32, device=self.device) if want_dec else None
         dp = ctypes.POINTER(ctypes.c_double)
-        _lib.check(self.lib.eav_preproc_run(ctypes.byref(c), _ptr(raw), taps.ctypes.data_as(dp), sos.ctypes.data_as(dp),
-                                            _ptr(epoch_slot), int(n_epochs_out), _ptr(epochs), _ptr(dec),
-                                            _ptr(self.workspace), self.ws_bytes, _stream()), "eav_preproc_run")
+        with _on(self.device):
+            _lib.check(self.lib.eav_preproc_run(ctypes.byref(c), _ptr(raw), taps.ctypes.data_as(dp), sos.ctypes.data_as(dp),
+                                                _ptr(epoch_slot), int(n_epochs_out), _ptr(epochs), _ptr(dec),
+                                                _ptr(self.workspace), self.ws_bytes, _stream()), "eav_preproc_run")
         return (epochs, dec) if want_dec else epochs

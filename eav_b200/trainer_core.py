@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import EAV_DROPOUT_MASK, EAV_DROPOUT_NONE, EAV_DROPOUT_PHILOX
-from .ops import EegnetDims, _ptr, _stream
+from .ops import EegnetDims, _on, _ptr, _stream
 
 
 class _Program:
@@ -48,12 +48,16 @@ class _Program:
         elif self.mask1 is not None:
             mode = EAV_DROPOUT_MASK
         else:
-            mode = EAV_DROPOUT_PHILOX
+            mode = c.dims.philox_mode
         return c.dims.cfg(c.M, self.B, self.bn_train, mode, c.pstride, c.dims.n_bn, seed=c.seed, step=0,
-                          step_ptr=c.step_dev.data_ptr() if mode == EAV_DROPOUT_PHILOX else 0)
+                          step_ptr=c.step_dev.data_ptr() if mode >= EAV_DROPOUT_PHILOX else 0)
 
     def enqueue(self):
-        """Issue one step on the current stream (capturable: only kernel launches)."""
+        """Issue one step on the current stream of the trainer's device (capturable: only kernel launches)."""
+        with _on(self.core.device):
+            self._enqueue()
+
+    def _enqueue(self):
         c, lib = self.core, self.core.lib
         cfg = self.cfg()
         x = self.x_src if self.x_src is not None else c.x
@@ -74,6 +78,10 @@ class _Program:
                                                c.eps, st), "eav_adam_step_graph")
 
     def capture(self):
+        with _on(self.core.device):
+            self._capture()
+
+    def _capture(self):
         # warm up on a side stream (sets kernel attributes, allocates nothing), then capture
         step_before = self.core.step_dev.clone()
         snap = self.core.snapshot()
@@ -182,6 +190,17 @@ class SubjectBatchTrainer:
     def restore(self, snap):
         for t, s in zip((self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.bn_state), snap):
             t.copy_(s)
+
+    def set_lr(self, lr):
+        """New learning rate for every later step (the value is a launch argument baked into captured graphs, so the
+        train programs are re-captured on their next use)."""
+        lr = float(lr)
+        if lr == self.lr:
+            return
+        self.lr = lr
+        for p in self._programs.values():
+            if p.kind == "train":
+                p.graph = None
 
     # ----------------------------------------------------------------- steps
     def program(self, B, bn_train, kind="train"):
@@ -299,6 +318,11 @@ class EpochRunner:
         c = self.core
         sched = self.sched if sched is None else sched
         epoch_dev = self.epoch_dev if epoch_dev is None else epoch_dev
+        with _on(c.device):
+            self._enqueue_schedule(sched, epoch_dev)
+
+    def _enqueue_schedule(self, sched, epoch_dev):
+        c = self.core
         _lib.check(c.lib.eav_epoch_schedule(_ptr(sched), _ptr(self.subject_ids), c.M, self.n_train, self.batch,
                                             self.rows_per_model, self.train_first_row, self.seed, _ptr(epoch_dev),
                                             _stream()), "eav_epoch_schedule")
@@ -313,6 +337,10 @@ class EpochRunner:
 
     def enqueue(self, bn_train):
         """Issue one whole epoch on the current stream (kernel launches only: capturable)."""
+        with _on(self.core.device):
+            self._enqueue(bn_train)
+
+    def _enqueue(self, bn_train):
         c, lib = self.core, self.core.lib
         self.enqueue_schedule()
         for s, Bs in enumerate(self.train_sizes):
@@ -346,6 +374,10 @@ class EpochRunner:
 
     def capture(self, bn_train):
         """Warm-up (really runs one epoch on a side stream), capture, roll every piece of state back."""
+        with _on(self.core.device):
+            return self._capture(bn_train)
+
+    def _capture(self, bn_train):
         snap = [t.clone() for t in self._state()]
         s = torch.cuda.Stream(device=self.core.device)
         s.wait_stream(torch.cuda.current_stream())

@@ -101,6 +101,8 @@ int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, const double *t
 #define EAV_DROPOUT_NONE  0 /* eval mode or p == 0                                 */
 #define EAV_DROPOUT_MASK  1 /* caller supplies keep-masks (uint8 1/0): parity mode */
 #define EAV_DROPOUT_PHILOX 2/* on-device Philox4x32-10 keyed by (seed, element)   */
+#define EAV_DROPOUT_PHILOX_2D 3 /* nn.Dropout2d (dropoutType != 'Dropout', EEGNet_tor.py:21): one on-device
+                                   Philox draw per (sample, channel) row, the whole row kept or zeroed */
 
 typedef struct eav_eegnet_cfg {
     int32_t n_models;      /* M                                                  */
@@ -291,7 +293,7 @@ int eav_measure_fp32_peak_mode(int mode, double *tflops, void *stream);
  *   call_base_dev (optional): device-resident step counter s; the effective call number is s * calls_per_step + call
  *   with call in 1..calls_per_step, so that a captured CUDA graph of a whole training step replays correctly.
  * All ranks must issue the same calls in the same order; a rank that never arrives makes the others trap after a
- * bounded spin instead of hanging. */
+ * wall-time bound (120 s) instead of hanging. */
 #define EAV_PEER_MAX_WORLD 16
 #define EAV_PEER_MAX_CTAS 64
 size_t eav_peer_exchange_bytes(size_t slot_bytes);

@@ -72,3 +72,37 @@ def test_prefetcher_propagates_errors(tmp_path):
     _write_subject(tmp_path, 1, rng)
     with pytest.raises(FileNotFoundError):
         list(MI.SubjectPrefetcher(str(tmp_path), [1, 2], device=None))
+
+
+def _mat5_double_stored_as_int16(path, name, values):
+    """A MAT-file v5 whose mxDOUBLE array `name` has its real part STORED as miINT16 (MATLAB's numeric data
+    compression): hand-assembled, since scipy.io.savemat never writes that form."""
+    import struct
+    vals = np.asarray(values)
+    dims = vals.shape
+    body = struct.pack("<II", 6, 8) + struct.pack("<II", 6, 0)                     # array flags: class mxDOUBLE (6)
+    body += struct.pack("<II", 5, 4 * len(dims)) + struct.pack("<%di" % len(dims), *dims)
+    body += b"\0" * ((-4 * len(dims)) % 8)
+    nm = name.encode()
+    body += struct.pack("<II", 1, len(nm)) + nm + b"\0" * ((-len(nm)) % 8)
+    data = np.asfortranarray(vals).astype("<i2").tobytes(order="F")
+    body += struct.pack("<II", 3, len(data)) + data + b"\0" * ((-len(data)) % 8)   # miINT16 payload
+    head = b"MATLAB 5.0 MAT-file, hand-made".ljust(116) + b"\0" * 8 + struct.pack("<H", 0x0100) + b"IM"
+    with open(path, "wb") as f:
+        f.write(head + struct.pack("<II", 14, len(body)) + body)
+
+
+def test_double_array_stored_as_int16_matches_loadmat_defaults(tmp_path):
+    """ADVICE r1 asked for float64 here; scipy.io.loadmat with its defaults (what the reference calls,
+    Dataload_eeg.py:70) returns the STORAGE dtype for such an array, and the reader must agree with loadmat."""
+    vals = np.arange(4 * 3 * 2).reshape(4, 3, 2) - 7
+    folder = tmp_path / "subject01" / "EEG"
+    folder.mkdir(parents=True)
+    path = str(folder / "subject01_eeg.mat")
+    _mat5_double_stored_as_int16(path, "seg", vals)
+    ref = scipy.io.loadmat(path)["seg"]
+    assert np.array_equal(ref, vals)
+    arr, _, zero_copy = MI.read_mat_array(path, ("seg",))
+    assert zero_copy and arr.dtype == ref.dtype                                # int16, like loadmat's default
+    assert np.array_equal(np.transpose(np.asarray(arr), (2, 1, 0)), ref)
+    assert scipy.io.loadmat(path, mat_dtype=True)["seg"].dtype == np.float64   # (the class dtype needs mat_dtype=True)
