@@ -393,6 +393,103 @@ int launch_reduce_partials(const float *part, int n_part, int64_t len, int n_mod
 // Variant 1 block-2 backward: pointwise conv then depthwise temporal conv.
 // =================================================================================
 // dy3d[n,g,u] = sum_o W3p[o,g] * dy3[n,o,u];   per-sample partial dW3p[n][o][g] = sum_u dy3[n,o,u]*y3d[n,g,u]
+//
+// Fast path (F2, G <= 64, T4 <= 128: the EAV shape is 64 x 64 x 125).  One CTA per sample stages dy3 (BatchNorm-3
+// backward applied on load), its transpose, y3d and the 16 KB weight matrix in shared memory once; both small GEMMs
+// (2 x 0.5 MFLOP per sample) then run from shared memory with register tiles:
+//   phase 1  warp = 8 channels g, lane = 4 positions u (acc[8][4]); per o: 2 broadcast LDS.128 + 4 LDS per 32 FFMA
+//   phase 2  thread = (channel g, 16 outputs o) (acc[16]); per u: 1 LDS + 4 broadcast LDS.128 per 16 FFMA
+// Row pitch 129 keeps the lane-varying reads conflict free.  (The first version read y3d straight from global memory
+// with a stride of T4 floats between lanes and re-staged nothing: 2.36 ms per step at 1344 samples, now ~0.1 ms.)
+constexpr int PWB_P = 129, PWB_W = 64, PWB_THREADS = 256;
+
+__global__ void __launch_bounds__(PWB_THREADS)
+pw_bwd_tiled_kernel(const float *__restrict__ dz3, const float *__restrict__ y3, const float4 *__restrict__ bnf,
+                    const float4 *__restrict__ bnb, int bn_train, const float *__restrict__ y3d,
+                    const float *__restrict__ params, int64_t pstride, int64_t oW3p, int B, int G, int F2, int L,
+                    float *__restrict__ dy3d, float *__restrict__ part) {
+    extern __shared__ __align__(16) float sm[];
+    float *dys = sm;                         // [64][PWB_P]   dy3, rows >= F2 / columns >= L zero
+    float *as = dys + 64 * PWB_P;            // [64][PWB_P]   y3d
+    float *dyT = as + 64 * PWB_P;            // [128][PWB_W]  dy3 transposed
+    float *wsh = dyT + 128 * PWB_W;          // [64][PWB_W]   W3p[o][g]
+    const int n = blockIdx.x, m = n / B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 64 * PWB_P; i += PWB_THREADS) { dys[i] = 0.f; as[i] = 0.f; }
+    for (int i = tid; i < 128 * PWB_W; i += PWB_THREADS) dyT[i] = 0.f;
+    for (int i = tid; i < 64 * PWB_W; i += PWB_THREADS) wsh[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < F2 * L; i += PWB_THREADS) {
+        const int o = i / L, u = i - o * L;
+        const int64_t idx = (int64_t)n * F2 * L + i;
+        float v = dz3[idx];
+        const float4 kb = bnb[(int64_t)m * F2 + o];
+        if (bn_train) {
+            const float4 kf = bnf[(int64_t)m * F2 + o];
+            v = kb.x * (v - kb.y - (y3[idx] - kf.x) * kf.y * kb.z);
+        } else {
+            v = kb.x * v;
+        }
+        dys[o * PWB_P + u] = v;
+        dyT[u * PWB_W + o] = v;
+    }
+    for (int i = tid; i < G * L; i += PWB_THREADS) {
+        const int g = i / L, u = i - g * L;
+        as[g * PWB_P + u] = y3d[(int64_t)n * G * L + i];
+    }
+    const float *W = params + (int64_t)m * pstride + oW3p;
+    for (int i = tid; i < F2 * G; i += PWB_THREADS) wsh[(i / G) * PWB_W + (i % G)] = W[i];
+    __syncthreads();
+    {   // phase 1: dy3d[g][u] = sum_o W[o][g] * dy[o][u]
+        float acc[8][4];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+        const int g0 = 8 * warp;
+        for (int o = 0; o < F2; ++o) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(wsh + o * PWB_W + g0);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wsh + o * PWB_W + g0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            float dv[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dv[b] = dys[o * PWB_P + lane + 32 * b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(w[a], dv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int g = g0 + a, u = lane + 32 * b;
+                if (g < G && u < L) dy3d[((int64_t)n * G + g) * L + u] = acc[a][b];
+            }
+    }
+    {   // phase 2: part[n][o][g] = sum_u dy[o][u] * y3d[g][u]
+        const int g = tid & 63, o0 = (tid >> 6) * 16;
+        float acc[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) acc[a] = 0.f;
+        for (int u = 0; u < L; ++u) {
+            const float av = as[g * PWB_P + u];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 d4 = *reinterpret_cast<const float4 *>(dyT + u * PWB_W + o0 + 4 * q);
+                acc[4 * q] = fmaf(d4.x, av, acc[4 * q]);
+                acc[4 * q + 1] = fmaf(d4.y, av, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(d4.z, av, acc[4 * q + 2]);
+                acc[4 * q + 3] = fmaf(d4.w, av, acc[4 * q + 3]);
+            }
+        }
+        if (g < G) {
+#pragma unroll
+            for (int a = 0; a < 16; ++a)
+                if (o0 + a < F2) part[((int64_t)n * F2 + o0 + a) * G + g] = acc[a];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 pw_bwd_kernel(const float *__restrict__ dz3, const float *__restrict__ y3, const float4 *__restrict__ bnf,
               const float4 *__restrict__ bnb, int bn_train, const float *__restrict__ y3d,
@@ -443,8 +540,20 @@ int launch_pw_bwd(const NetDims &d, const float *dz3, const float *y3, const flo
         cudaFuncSetAttribute(pw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    pw_bwd_kernel<<<d.N, 128, smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, y3d, params, d.pstride, d.oW3p, d.B,
-                                          d.G, d.F2, d.T4, dy3d, part);
+    if (d.F2 <= 64 && d.G <= 64 && d.T4 <= 128) {
+        const size_t tsm = (size_t)(2 * 64 * PWB_P + 128 * PWB_W + 64 * PWB_W) * sizeof(float);
+        static PerDevice<bool> tiled_attr_pd(false);
+        bool &tiled_attr = tiled_attr_pd.here();
+        if (!tiled_attr) {
+            cudaFuncSetAttribute(pw_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+            tiled_attr = true;
+        }
+        pw_bwd_tiled_kernel<<<d.N, PWB_THREADS, tsm, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, y3d, params, d.pstride,
+                                                          d.oW3p, d.B, d.G, d.F2, d.T4, dy3d, part);
+    } else {
+        pw_bwd_kernel<<<d.N, 128, smem, st>>>(dz3, y3, bnf3, bnb3, d.bn_train, y3d, params, d.pstride, d.oW3p, d.B,
+                                              d.G, d.F2, d.T4, dy3d, part);
+    }
     EAV_CUDA_LAUNCH_CHECK("pw_bwd");
     return launch_reduce_partials(part, d.B, (int64_t)d.F2 * d.G, d.M, d.pstride, grads + d.oW3p, st);
 }

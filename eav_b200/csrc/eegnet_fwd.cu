@@ -867,10 +867,84 @@ pw_fwd_kernel(const float *__restrict__ y3d, const float *__restrict__ params, i
     }
 }
 
+// Tiled variant for F2, G <= 64 and T4 <= 128 (the EAV shape): one CTA per sample stages y3d once (the kernel above
+// makes every (sample, output channel) CTA re-read the sample's 32 KB of y3d: 64x the L2 traffic); warp = 8 output
+// channels, lane = 4 positions, acc[8][4]; per input channel 2 broadcast LDS.128 + 4 LDS per 32 FFMA.
+constexpr int PWF_P = 129, PWF_W = 64;
+__global__ void __launch_bounds__(256)
+pw_fwd_tiled_kernel(const float *__restrict__ y3d, const float *__restrict__ params, int64_t pstride,
+                    int64_t oW3p, int B, int G, int F2, int L, float *__restrict__ y3, float *__restrict__ part) {
+    extern __shared__ __align__(16) float sm[];
+    float *as = sm;                  // [64][PWF_P]  y3d, zero padded
+    float *wt = as + 64 * PWF_P;     // [64][PWF_W]  W3p transposed: wt[g][o]
+    const int n = blockIdx.x, m = n / B, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 64 * PWF_P; i += 256) as[i] = 0.f;
+    for (int i = tid; i < 64 * PWF_W; i += 256) wt[i] = 0.f;
+    __syncthreads();
+    for (int i = tid; i < G * L; i += 256) {
+        const int g = i / L, u = i - g * L;
+        as[g * PWF_P + u] = y3d[(int64_t)n * G * L + i];
+    }
+    const float *W = params + (int64_t)m * pstride + oW3p;
+    for (int i = tid; i < F2 * G; i += 256) wt[(i % G) * PWF_W + (i / G)] = W[i];
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int o0 = 8 * warp;
+    for (int g = 0; g < G; ++g) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(wt + g * PWF_W + o0);
+        const float4 w1 = *reinterpret_cast<const float4 *>(wt + g * PWF_W + o0 + 4);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float xv[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) xv[b] = as[g * PWF_P + lane + 32 * b];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(w[a], xv[b], acc[a][b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int o = o0 + a;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int u = lane + 32 * b;
+            if (o < F2 && u < L) {
+                y3[((int64_t)n * F2 + o) * L + u] = acc[a][b];
+                s1 += acc[a][b];
+                s2 = fmaf(acc[a][b], acc[a][b], s2);
+            }
+        }
+        if (part != nullptr) {
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            if (lane == 0 && o < F2) {
+                part[((int64_t)n * F2 + o) * 2] = s1;
+                part[((int64_t)n * F2 + o) * 2 + 1] = s2;
+            }
+        }
+    }
+}
+
 int launch_pw_fwd(const NetDims &d, const float *y3d, const float *params, float *y3, float *part,
                   int *part_rows, cudaStream_t st) {
-    pw_fwd_kernel<<<dim3(d.F2, d.N), 128, (size_t)d.G * sizeof(float), st>>>(y3d, params, d.pstride, d.oW3p,
-                                                                           d.B, d.G, d.F2, d.T4, y3, part);
+    if (d.F2 <= 64 && d.G <= 64 && d.T4 <= 128) {
+        const size_t tsm = (size_t)(64 * PWF_P + 64 * PWF_W) * sizeof(float);
+        static PerDevice<bool> attr_pd(false);
+        bool &attr = attr_pd.here();
+        if (!attr) {
+            cudaFuncSetAttribute(pw_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+            attr = true;
+        }
+        pw_fwd_tiled_kernel<<<d.N, 256, tsm, st>>>(y3d, params, d.pstride, d.oW3p, d.B, d.G, d.F2, d.T4, y3, part);
+    } else {
+        pw_fwd_kernel<<<dim3(d.F2, d.N), 128, (size_t)d.G * sizeof(float), st>>>(y3d, params, d.pstride, d.oW3p,
+                                                                               d.B, d.G, d.F2, d.T4, y3, part);
+    }
     EAV_CUDA_LAUNCH_CHECK("pw_fwd");
     if (part_rows) *part_rows = d.B;
     return 0;

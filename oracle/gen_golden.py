@@ -354,9 +354,91 @@ def gen_shallow():
     save("shallowconvnet_b4.npz", **out)
 
 
+def gen_bench_config(ns):
+    """The benchmark's own configuration through the UNMODIFIED reference: one full subject,
+    280 / 120 epochs, batch 32 (9 steps per epoch, the last one ragged: 24), lr 1e-5, 2 epochs -- epoch 1 in train
+    mode, epoch 2 in eval mode.  Records every step's batch rows, dropout masks and loss, the validation
+    batch losses and the printed lines."""
+    M = ns.EEGNet_tor
+    torch.manual_seed(21)
+    model = ref_shim.make_eegnet_tor(ns, 5)
+    trx, try_, tex, tey = GI.bench_subject_inputs()
+    out = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    out["input_checksum"] = GI.checksum(trx, try_, tex, tey)
+    trainer = M.Trainer_uni(model, [trx, try_, tex, tey], lr=1e-5, batch_size=32, num_epochs=2,
+                            device=torch.device("cpu"))
+    crit0 = trainer.criterion
+    step_losses, batch_rows, masks1, masks2 = [], [], [], []
+    marker = {float(v): i for i, v in enumerate(trx[:, 0, 0, 0])}
+    assert len(marker) == 280
+
+    def pre_hook(mod, args):
+        if torch.is_grad_enabled():
+            batch_rows.append(np.array([marker[float(v)] for v in args[0][:, 0, 0, 0]], dtype=np.int32))
+    model.register_forward_pre_hook(pre_hook)
+
+    def drop_hook(mod, inp, outp):          # keep-mask of this call, recovered from the reference's own output
+        if mod.training:
+            (masks1 if outp.shape[-1] == 125 else masks2).append((outp != 0).numpy().reshape(outp.shape[0], 64, -1))
+    model.dropout.register_forward_hook(drop_hook)
+
+    class Rec(torch.nn.Module):
+        def forward(self, s, t):
+            l = crit0(s, t)
+            step_losses.append((float(l.detach()), bool(torch.is_grad_enabled())))
+            return l
+    trainer.criterion = Rec()
+    torch.manual_seed(78)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        trainer.train()
+    out["train_step_loss"] = np.array([l for l, ge in step_losses if ge])
+    out["val_batch_loss"] = np.array([l for l, ge in step_losses if not ge])
+    assert out["train_step_loss"].shape == (18,) and out["val_batch_loss"].shape == (8,)
+    assert [len(r) for r in batch_rows] == ([32] * 8 + [24]) * 2 and len(masks1) == 9 and len(masks2) == 9
+    out["batch_rows"] = np.concatenate(batch_rows)
+    # ELU'd + pooled activations are never exactly 0, so (output != 0) IS the keep-mask
+    out["mask1_bits"] = np.packbits(np.concatenate([m.reshape(-1) for m in masks1]))
+    out["mask2_bits"] = np.packbits(np.concatenate([m.reshape(-1) for m in masks2]))
+    out["stdout"] = np.array(buf.getvalue())
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k or k in ("firstBN.weight", "dense.bias"):
+            out[f"final::{k}"] = v.detach().numpy().copy()
+    save("trainer_uni_bench_2ep.npz", **out)
+
+    # EEGNetTrainer.train() (CNN_EEG.py:70-146): 2 epochs, model.train() every epoch, logits + CE, Adam lr 1e-3
+    C = ns.CNN_EEG
+    torch.manual_seed(22)
+    model = C.EEGNet(nb_classes=4, Chans=64, Samples=128, dropoutRate=0.25)
+    trx, try_, tex, tey = GI.cnn_trainer_inputs()
+    out = {f"init::{k}": v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    out["input_checksum"] = GI.checksum(trx.numpy(), try_.numpy(), tex.numpy(), tey.numpy())
+    from torch.utils.data import TensorDataset
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tr = C.EEGNetTrainer(model, TensorDataset(trx, try_), TensorDataset(tex, tey), batch_size=32, epochs=2, lr=1e-3)
+        tr.device = torch.device("cpu")
+        tr.model.to("cpu")
+        torch.manual_seed(79)
+        tl1 = tr.train_epoch(); v1 = tr.validate_epoch()
+        tl2 = tr.train_epoch(); v2 = tr.validate_epoch()
+        pred = tr.predict()
+    out["train_loss"] = np.array([tl1, tl2])
+    out["val_loss"] = np.array([v1[0], v2[0]])
+    out["val_acc"] = np.array([v1[1], v2[1]])
+    out["predict"] = np.array(pred, dtype=np.int64)
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out[f"final::{k}"] = v.detach().numpy().copy()
+    save("cnn_eeg_trainer_2ep.npz", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "--only-bench-config" in sys.argv:
+        gen_bench_config(ref_shim.load())
+        sys.exit(0)
     if "--only-legacy" in sys.argv:
         gen_legacy()
         sys.exit(0)
@@ -369,3 +451,4 @@ if __name__ == "__main__":
     gen_eegnet_tor(ns)
     gen_cnn_eeg(ns)
     gen_shallow()
+    gen_bench_config(ns)

@@ -188,6 +188,23 @@ def test_trainer_uni_loop_vs_reference(golden):
     assert int(buffers["firstBN.num_batches_tracked"]) == 3          # only epoch 1 trains BN (F5)
 
 
+def test_trainer_uni_bench_configuration_vs_reference(golden):
+    """The benchmark's own configuration (one full subject, 280/120, batch 32 incl. the ragged 24, lr 1e-5, epoch 1
+    train mode + epoch 2 eval mode) pins the oracle where bench.py runs (VERDICT r1 next #4)."""
+    g = golden("trainer_uni_bench_2ep.npz")
+    data = GI.bench_subject_inputs()
+    assert np.allclose(GI.checksum(*data), g["input_checksum"], rtol=1e-12)
+    params, buffers = _init(g, "tor")
+    torch.manual_seed(78)
+    log = EO.trainer_uni_train(params, buffers, data, lr=1e-5, batch_size=32, num_epochs=2)
+    ref = g["train_step_loss"]
+    assert len(log["step_loss"]) == ref.size == 18
+    assert np.abs(np.array(log["step_loss"]) - ref).max() < 1e-4 * np.abs(ref).max()
+    vref = g["val_batch_loss"].reshape(2, 4).mean(1)
+    assert np.allclose([v[0] for v in log["val"]], vref, rtol=1e-4)
+    assert int(buffers["firstBN.num_batches_tracked"]) == 9          # the 9 steps of epoch 1 only (F5)
+
+
 @pytest.mark.parametrize("tag", ["default", "eav"])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_cnn_eeg_fwd_bwd_vs_reference(golden, tag, mode):
