@@ -118,10 +118,11 @@ WsLayout make_ws_layout(const NetDims &d) {
     pa = max_sz(pa, N * 2 * d.F2);                                        // pw_fwd / tail_bwd
     pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
     pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
+    pa = max_sz(pa, (size_t)d.M * 128 * 2 * d.F1);                        // fused block-1 backward: [M][S <= 128][F1][2]
     w.part = take(pa);
     // weight-gradient partials, one region per layer (the block-2 kernels run on a forked stream)
     w.partw = take((size_t)d.M * tconv_dw_ctas_per_model(d) * d.F1 * d.K1);        // tconv_bwd_dw
-    w.partw2 = take(N * d.G * d.C);                                                // dw_bwd
+    w.partw2 = take(max_sz(N * d.G * d.C, tconv_bwd_fused_shape_ok(d) ? tconv_bwd_fused_partw2_floats(d) : 0));   // dw_bwd / fused block-1 backward
     if (d.variant == EAV_VARIANT_TOR) w.partw3 = take((size_t)d.M * sepconv_dw_splits(d) * d.F2 * d.G * 16);
     else w.partw3 = take(max_sz(N * d.F2 * d.G, N * d.G * d.K2));
     w.dz3 = take(N * d.F2 * d.T4);
@@ -303,11 +304,22 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_BN2_BWD:
             return launch_bn_bwd_finalize(d, 2, part, d.B, W * d.B * d.T, dp_bn ? sums(2, true) : nullptr, a.params, WS(float4, w.bnf2), WS(float4, w.bnb2), a.grads, st);
         case ST_DW_BWD:
+            if (tconv_bwd_fused_ok(d)) return 0;     // eval mode: regenerated inside the tconv_bwd_dw stage
             return launch_dw_bwd(d, WS(float, w.dz2), WS(float, w.y2), WS(float4, w.bnf2), WS(float4, w.bnb2), WS(float, w.y1),
                                  WS(float4, w.bnf1), a.params, WS(float, w.dz1), partw2, part, a.grads, st);
         case ST_BN1_BWD:
+            if (tconv_bwd_fused_ok(d)) return 0;     // its sums come out of the fused kernel: finalized in that stage
             return launch_bn_bwd_finalize(d, 1, part, d.B, W * d.B * d.C * d.T, dp_bn ? sums(1, true) : nullptr, a.params, WS(float4, w.bnf1), WS(float4, w.bnb1), a.grads, st);
         case ST_TCONV_BWD_DW:
+            if (tconv_bwd_fused_ok(d)) {
+                // eval-mode BN: ONE pass over y1 produces dW1 (tcgen05), dW2 and the BatchNorm-1 gradient sums
+                const int S = tconv_bwd_dw_tc_splits(d);
+                TRY(launch_tconv_bwd_fused_tc(d, a.x, a.x_index, WS(float, w.dz2), WS(float, w.y1), WS(float4, w.bnf1),
+                                              WS(float4, w.bnf2), a.params, partw, partw2, part, a.grads, S, st));
+                TRY(launch_reduce_partials(partw, S, (int64_t)d.F1 * d.K1, d.M, d.pstride, a.grads + d.oW1, st));
+                return launch_bn_bwd_finalize(d, 1, part, S, W * d.B * d.C * d.T, nullptr, a.params, WS(float4, w.bnf1),
+                                              WS(float4, w.bnb1), a.grads, st);
+            }
             return launch_tconv_bwd_dw(d, a.x, a.x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
                                        partw, a.grads, st);
         default: break;

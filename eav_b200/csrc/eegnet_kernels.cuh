@@ -84,6 +84,14 @@ int tconv_bwd_dw_tc_splits(const NetDims &d);     // partial slabs per model wri
 int launch_tconv_bwd_dw_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *dz1,
                            const float *y1, const float4 *bnf1, const float4 *bnb1, float *part, int S,
                            cudaStream_t st);
+// eval-mode fused backward of block 1 (tconv_tc.cu): dz1 regenerated from dz2 + y1 inside the dW1 kernel, which also
+// produces dW2 and the BatchNorm-1 backward sums (replaces dw_bwd + tconv_bwd_dw; no dz1 round trip through HBM)
+bool tconv_bwd_fused_ok(const NetDims &d);          // this launch takes the fused path (eval-mode BN only)
+bool tconv_bwd_fused_shape_ok(const NetDims &d);    // ... could take it in eval mode (workspace sizing)
+size_t tconv_bwd_fused_partw2_floats(const NetDims &d);
+int launch_tconv_bwd_fused_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *dz2,
+                              const float *y1, const float4 *bnf1, const float4 *bnf2, const float *params,
+                              float *part, float *partw2, float *partbn, float *grads, int S, cudaStream_t st);
 int tconv_fwd_rows_per_sample(const NetDims &d);   // BN1 partial rows per sample written by tconv_fwd
 int sepconv_fwd_rows_per_model(const NetDims &d);   // BN3 partial rows per model written by sepconv_fwd
 int dw_fwd_tiles(const NetDims &d);   // time tiles per (sample, filter) of dw_fwd == BN2 partial rows per sample

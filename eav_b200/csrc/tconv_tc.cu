@@ -606,6 +606,433 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
 
 }  // namespace
 
+// =============================================================================================
+// Eval-mode fused backward of block 1 (EEGNet_tor.py:51-57 backward; SURVEY 8a rows M1-M4, section 7: "[dz1] can be
+// regenerated in-register inside the dW1 kernel").  Same MMA formulation as tconv_bwd_dw_tc_kernel, but the producers
+// no longer READ the (N,8,30,500) gradient dz1 that dw_bwd used to write: they rebuild it from the 16x smaller dz2 and
+// the saved conv output y1 while staging the MMA operand,
+//     dz1[f][c][t] = E'(pre) * sum_d k2[g] W2[g][c] dz2[g][t],   g = 8 f + d,  pre = y1*scale1[f] + shift1[f],
+// and fold in everything else dw_bwd did in the same pass over y1:
+//     dW2[g][c] = k2[g] * sum_{b,t} dz2[g][t] * act(pre),    d(beta1)[f] = sum dz1,   d(gamma1)[f] = sum dz1 * xhat1.
+// Eval-mode BatchNorm only (the reference's steady state): BN backward is then the per-channel scale
+// k = gamma*invstd with no batch sums, so nothing has to be known before this kernel starts.  k1[f] is applied to the
+// dW1 slab in the epilogue.  This deletes one 645 MB write, one 645 MB read and the dw_bwd launch per step.
+//
+// Producers: 8 warps = 4 time quarters (lane owns 4 consecutive t) x 2 filter pairs, ALL on the same row; a thread
+// keeps dz2 of its 2 filters x 8 depth channels x 4 time steps in 64 registers for the 30 rows of a sample, so the
+// per-row inputs are one 128-bit load of x and two of y1.  The 16 dW2 accumulators of a row are summed across the
+// warp with a transposing butterfly (16 shuffles) and added to a per-(quarter, electrode) shared-memory slot owned
+// by that warp: every sum has a fixed order (deterministic, like all other reductions of the library).
+// =============================================================================================
+namespace {
+
+constexpr int TCX_PROD_WARPS = 8;
+constexpr int TCX_THREADS = 16 * 32;     // 4 epilogue + 8 producer + MMA + loader warp + 2 idle warps completing the last warpgroup
+constexpr int TCX_STAGES = 5;
+constexpr int TCX_CMAX = 32;                               // electrodes the shared-memory tables hold
+constexpr int TCX_NB = 3;                                  // input row buffers (TMA prefetch depth)
+constexpr int TCX_INROW = 512;                             // floats per staged row (x, y1 of 4 filters): 5 rows per buffer
+constexpr size_t TCX_SMEM_FLOATS = (size_t)TCX_STAGES * TCW_STAGE_FLOATS + 384 * TCW_SP + TCX_CMAX * 32 +
+                                   4 * TCX_CMAX * 32 + TCX_PROD_WARPS * 4 + TCX_NB * 5 * TCX_INROW;
+
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TCX_PROD_WARPS * 32) : "memory"); }
+
+// Sums v[0..15] over the 32 lanes; afterwards lane L holds the total of index 8*b16 + 4*b8 + 2*b4 + b2 (b = bits of L).
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#define EAV_TR_STEP(HALF, BIT)                                                         \
+    {                                                                                  \
+        const bool upper = (lane & BIT) != 0;                                          \
+        _Pragma("unroll") for (int i = 0; i < HALF; ++i) {                             \
+            const float send = upper ? v[i] : v[i + HALF];                             \
+            const float keep = upper ? v[i + HALF] : v[i];                             \
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, BIT);                     \
+        }                                                                              \
+    }
+    EAV_TR_STEP(8, 16)
+    EAV_TR_STEP(4, 8)
+    EAV_TR_STEP(2, 4)
+    EAV_TR_STEP(1, 2)
+#undef EAV_TR_STEP
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct FusedBwdArgs {
+    const float *dz2;          // [N][G][T]   gradient w.r.t. the BatchNorm-2 output
+    const float *y1;           // [N][F1][C][T] saved raw conv output
+    const float4 *bnf1, *bnf2; // {mean, invstd, scale, shift} per (model, channel)
+    const float *params;
+    int64_t pstride, oW2, og1, og2;
+    float *part;               // dW1 partial slabs [M][S][F1][K1]
+    float *partw2;             // dW2 partial sums  [M*S][2 fg][4 quarters][TCX_CMAX][32]
+    float *partbn;             // BatchNorm-1 backward sums [M][S][F1][2]
+    int elu1;                  // 1: ELU after BN1 (EEGNet_tor), 0: none (CNN_EEG)
+};
+
+// Register budget: the producers need ~150 registers (64 for the resident dz2 alone), the epilogue and the MMA warp
+// far fewer, and 13 warps x 150 do not fit an SM (a sub-partition owns 16 384 registers and every fourth warp).
+// Roles therefore sit on warpgroup boundaries -- warps 0-3 epilogue, 4-11 producers, 12 MMA issue, 13 TMA loader,
+// 14-15 idle (setmaxnreg.sync.aligned is a warpgroup-wide instruction: a partial last group hangs the inc) -- and
+// are rebalanced with setmaxnreg: the CTA launches with 512 x 128 registers, the epilogue drops to 80, the last
+// group to 40, the producers grow to 184.
+//
+// Inputs: the loader warp streams each row's x and the four y1 rows (10 KB) into a 3-deep shared-memory ring with
+// cp.async.bulk (TMA) two rows ahead; the producers only wait on an mbarrier and read 128-bit values from shared
+// memory.  (Register prefetch with plain loads did not work: the six hardware load scoreboards are shared with the
+// per-sample dz2 reload, ncu showed 31 % of the producers' time in long-scoreboard stalls on the first FFMA of a row,
+// and the per-thread 64-bit address arithmetic was ~15 % of the row's instructions.)
+__global__ void __launch_bounds__(TCX_THREADS, 1)
+tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ x_index, const FusedBwdArgs a,
+                          int M, int B, int C, int T, int K1, int padl, int S) {
+    extern __shared__ __align__(1024) float smem[];
+    float *ring = smem;                                            // [STAGES][STAGE_FLOATS]
+    float *diag = smem + TCX_STAGES * TCW_STAGE_FLOATS;            // [384][33]
+    float *vtab = diag + 384 * TCW_SP;                             // [CMAX][32]  k2[g] * W2[g][c], g = 32 fg + j
+    float *dw2s = vtab + TCX_CMAX * 32;                            // [4][CMAX][32]
+    float *bnred = dw2s + 4 * TCX_CMAX * 32;                       // [8][4]
+    float *inbuf = bnred + TCX_PROD_WARPS * 4;                     // [NB][5][INROW]: x, y1[f0..f3] of one row
+    __shared__ uint64_t bar_full[TCX_STAGES], bar_empty[TCX_STAGES], bar_accfull, bar_accempty, bar_epi;
+    __shared__ uint64_t bar_in_full[TCX_NB], bar_in_empty[TCX_NB];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F1 = 8, G = 64;
+    const int PADL = (padl + 3) & ~3, DELTA = PADL - padl;
+    const int mtiles = (K1 + 31 + DELTA + 127) / 128;
+    const int ksteps = (T + 255) / 256;
+    const int rows_m = B * C;
+    const int n_units = 2 * M * S;
+
+    if (tid == 0) {
+        for (int s = 0; s < TCX_STAGES; ++s) { tc::mbar_init(&bar_full[s], TCX_PROD_WARPS); tc::mbar_init(&bar_empty[s], 1); }
+        for (int s = 0; s < TCX_NB; ++s) { tc::mbar_init(&bar_in_full[s], 1); tc::mbar_init(&bar_in_empty[s], TCX_PROD_WARPS); }
+        tc::mbar_init(&bar_accfull, 1);
+        tc::mbar_init(&bar_accempty, 4);
+        tc::mbar_init(&bar_epi, 128);
+        tc::mbar_init_fence();
+    }
+    if (warp == 12) tc::tmem_alloc(&tmem_slot, 512);
+    for (int i = tid; i < TCX_STAGES * TCW_STAGE_FLOATS; i += TCX_THREADS) ring[i] = 0.f;   // halos / tails stay zero
+    for (int i = tid; i < 4 * TCX_CMAX * 32; i += TCX_THREADS) dw2s[i] = 0.f;
+    for (int i = tid; i < TCX_NB * 5 * TCX_INROW; i += TCX_THREADS) inbuf[i] = 0.f;         // [T, INROW) is never copied to
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+
+    auto unit_rows = [&](int u, int &m, int &fg, int &r_lo, int &r_hi) {
+        fg = u & 1;
+        const int ms = u >> 1;
+        m = ms / S;
+        const int sp = ms - m * S;
+        r_lo = (int)((int64_t)rows_m * sp / S);
+        r_hi = (int)((int64_t)rows_m * (sp + 1) / S);
+    };
+
+    if (warp >= 4 && warp < 12) {
+        // ---------------- producers ----------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+        const int pw = warp - 4, q = pw & 3, fp = pw >> 2, ptid = tid - 4 * 32;
+        const int t = 4 * (lane + 32 * q);
+        const bool tact = t < T;
+        float4 dzr[2][8];
+        int64_t cur_n = -1;
+        int s = 0, sfull = 0;          // ring stage and whether it has been used before / parity of its last use
+        uint32_t sphase = 0;
+        int ib = 0;
+        uint32_t iphase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int m, fg, r_lo, r_hi;
+            unit_rows(u, m, fg, r_lo, r_hi);
+            const float *prm = a.params + (int64_t)m * a.pstride;
+            producers_sync();                                    // everybody is done with the previous unit's table
+            for (int i = ptid; i < TCX_CMAX * 32; i += TCX_PROD_WARPS * 32) {
+                const int c = i >> 5, j = i & 31, gch = fg * 32 + j;
+                float v = 0.f;
+                if (c < C) v = prm[a.og2 + gch] * a.bnf2[(int64_t)m * G + gch].y * prm[a.oW2 + (int64_t)gch * C + c];
+                vtab[i] = v;
+            }
+            producers_sync();
+            float sc1[2], sh1[2], is1[2], nmi[2];                // BN1 scale, shift, invstd, -mean*invstd
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 st = a.bnf1[(int64_t)m * F1 + fg * 4 + fp * 2 + h];
+                sc1[h] = st.z; sh1[h] = st.w; is1[h] = st.y; nmi[h] = -st.x * st.y;
+            }
+            float p1[2] = {0.f, 0.f}, p2[2] = {0.f, 0.f};
+            int b = r_lo / C, c = r_lo - b * C;
+            for (int r = r_lo; r < r_hi; ++r) {
+                const int64_t n = (int64_t)m * B + b;
+                if (n != cur_n) {                                // a new sample: its dz2 stays in registers for C rows
+                    cur_n = n;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int dd = 0; dd < 8; ++dd) {
+                            const int gch = (fg * 4 + fp * 2 + h) * 8 + dd;
+                            dzr[h][dd] = tact ? *reinterpret_cast<const float4 *>(a.dz2 + (n * G + gch) * (int64_t)T + t)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
+                // this row's inputs, staged by the loader warp
+                tc::mbar_wait(&bar_in_full[ib], iphase);
+                const float *in = inbuf + (size_t)ib * 5 * TCX_INROW;
+                float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), yv[2];
+                if (fp == 0) xv = *reinterpret_cast<const float4 *>(in + t);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) yv[h] = *reinterpret_cast<const float4 *>(in + (1 + fp * 2 + h) * TCX_INROW + t);
+                float acc[16];
+                float4 outv[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float4 v0 = *reinterpret_cast<const float4 *>(vtab + c * 32 + fp * 16 + h * 8);
+                    const float4 v1 = *reinterpret_cast<const float4 *>(vtab + c * 32 + fp * 16 + h * 8 + 4);
+                    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const float yy[4] = {yv[h].x, yv[h].y, yv[h].z, yv[h].w};
+                    float oo[4];
+#pragma unroll
+                    for (int dd = 0; dd < 8; ++dd) acc[h * 8 + dd] = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float pre = fmaf(yy[e], sc1[h], sh1[h]);
+                        float ep = 1.f, act = pre;
+                        if (a.elu1) {
+                            const float ex = __expf(pre);
+                            const bool pos = pre > 0.f;
+                            ep = pos ? 1.f : ex;
+                            act = pos ? pre : ex - 1.f;
+                        }
+                        float uu = 0.f;
+#pragma unroll
+                        for (int dd = 0; dd < 8; ++dd) {
+                            const float dzv = e == 0 ? dzr[h][dd].x : e == 1 ? dzr[h][dd].y : e == 2 ? dzr[h][dd].z : dzr[h][dd].w;
+                            uu = fmaf(vv[dd], dzv, uu);
+                            acc[h * 8 + dd] = fmaf(dzv, act, acc[h * 8 + dd]);
+                        }
+                        const float dz = uu * ep;
+                        p1[h] += dz;
+                        p2[h] = fmaf(dz, fmaf(yy[e], is1[h], nmi[h]), p2[h]);
+                        oo[e] = dz;
+                    }
+                    outv[h] = make_float4(oo[0], oo[1], oo[2], oo[3]);
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_in_empty[ib]);          // the loader may refill this input buffer
+                if (++ib == TCX_NB) { ib = 0; iphase ^= 1u; }
+                if (sfull) tc::mbar_wait(&bar_empty[s], sphase ^ 1u);       // the MMAs of the stage's previous use retired
+                const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
+                if (tact) {
+                    if (fp == 0) {
+                        float4 h4, l4;
+                        split4(xv, h4, l4);
+                        const uint32_t ad = sbase + 4u * (uint32_t)(PADL + t);
+                        sts_f4(swz128_32(ad), h4);
+                        sts_f4(swz128_32(ad + 4u * TCW_XS), l4);
+                    }
+                    const uint32_t dybase = sbase + 4u * 2 * TCW_XS;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 h4, l4;
+                        split4(outv[h], h4, l4);
+                        const uint32_t ad = dybase + 4u * (uint32_t)((fp * 2 + h) * TCW_DYROW + t);
+                        sts_f4(swz128_32(ad), h4);
+                        sts_f4(swz128_32(ad + 4u * 4 * TCW_DYROW), l4);
+                    }
+                }
+                tc::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_full[s]);
+                if (++s == TCX_STAGES) { s = 0; sfull = 1; sphase ^= 1u; }
+                // dW2 of this row: 16 (filter, depth) sums over the warp's 128 time steps -> this warp's own slot
+                const float tot = transpose_reduce16(acc, lane);
+                if ((lane & 1) == 0) {
+                    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    float *slot = dw2s + (q * TCX_CMAX + c) * 32 + fp * 16 + idx;
+                    *slot += tot;
+                }
+                if (++c == C) { c = 0; ++b; }
+            }
+            // ---- end of unit: dW2 slots and BatchNorm-1 sums -> global partials (fixed order)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { p1[h] = warp_sum(p1[h]); p2[h] = warp_sum(p2[h]); }
+            if (lane == 0) { bnred[pw * 4 + 0] = p1[0]; bnred[pw * 4 + 1] = p2[0]; bnred[pw * 4 + 2] = p1[1]; bnred[pw * 4 + 3] = p2[1]; }
+            producers_sync();
+            const int sp = (u >> 1) - m * S;
+            float *pw2 = a.partw2 + (((int64_t)(m * S + sp) * 2 + fg) * 4) * TCX_CMAX * 32;
+            for (int i = ptid; i < 4 * TCX_CMAX * 32; i += TCX_PROD_WARPS * 32) {
+                pw2[i] = dw2s[i];
+                dw2s[i] = 0.f;
+            }
+            if (ptid < 8) {                                      // (fp, h, which) -> filter fg*4 + fp*2 + h
+                const int fp2 = ptid >> 2, hw = ptid & 3;
+                float sum = 0.f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) sum += bnred[(fp2 * 4 + qq) * 4 + hw];
+                const int f = fg * 4 + fp2 * 2 + (hw >> 1);
+                a.partbn[(((int64_t)m * S + sp) * F1 + f) * 2 + (hw & 1)] = sum;
+            }
+        }
+    } else if (warp >= 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+        if (warp == 12) {
+            // ---------------- MMA issuer (as in tconv_bwd_dw_tc_kernel) ----------------
+            const bool leader = tc::elect_one();
+            const uint32_t idesc = tc::idesc_tf32(128, 128, 1, 1);
+            int g = 0, nu = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+                int m, fg, r_lo, r_hi;
+                unit_rows(u, m, fg, r_lo, r_hi);
+                if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);
+                for (int r = r_lo; r < r_hi; ++r, ++g) {
+                    const int s = g % TCX_STAGES, use = g / TCX_STAGES;
+                    tc::mbar_wait(&bar_full[s], use & 1);
+                    tc::tc_fence_after_sync();
+                    if (leader) {
+                        const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
+                        const uint32_t xhi = sbase, xlo = sbase + 4u * TCW_XS;
+                        const uint32_t dyhi = sbase + 4u * 2 * TCW_XS, dylo = dyhi + 4u * 4 * TCW_DYROW;
+                        const uint32_t first = (r == r_lo) ? 0u : 1u;
+                        for (int mt = 0; mt < mtiles; ++mt) {
+                            const uint32_t d = tmem + mt * 128;
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                const uint32_t ao = mt * 512 + ks * 1024, bo = ks * 1024;
+                                const uint64_t ah = desc_mn_sw(xhi + ao, 128, 512), al = desc_mn_sw(xlo + ao, 128, 512);
+                                const uint64_t bh = desc_mn_sw(dyhi + bo, 4 * TCW_DYROW, 512);
+                                const uint64_t bl = desc_mn_sw(dylo + bo, 4 * TCW_DYROW, 512);
+                                tc::mma_tf32_ss(d, ah, bh, idesc, (ks > 0) ? 1u : first);
+                                tc::mma_tf32_ss(d, ah, bl, idesc, 1u);
+                                tc::mma_tf32_ss(d, al, bh, idesc, 1u);
+                            }
+                        }
+                        tc::mma_commit(&bar_empty[s]);
+                        if (r == r_hi - 1) tc::mma_commit(&bar_accfull);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp == 13 && lane == 0) {
+            // ---------------- loader: x row + the four y1 rows of (n, c) -> input ring, TMA bulk copies ----------------
+            const uint32_t row_bytes = (uint32_t)T * 4u;
+            int g = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int m, fg, r_lo, r_hi;
+                unit_rows(u, m, fg, r_lo, r_hi);
+                for (int r = r_lo; r < r_hi; ++r, ++g) {
+                    const int buf = g % TCX_NB, use = g / TCX_NB;
+                    const int b = r / C, c = r - b * C;
+                    const int64_t n = (int64_t)m * B + b;
+                    const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
+                    if (use > 0) tc::mbar_wait(&bar_in_empty[buf], (use - 1) & 1);
+                    float *dst = inbuf + (size_t)buf * 5 * TCX_INROW;
+                    tc::mbar_expect_tx(&bar_in_full[buf], 5u * row_bytes);
+                    tc::tma_load_1d(dst, x + (xrow * C + c) * (int64_t)T, row_bytes, &bar_in_full[buf]);
+#pragma unroll
+                    for (int fl = 0; fl < 4; ++fl)
+                        tc::tma_load_1d(dst + (1 + fl) * TCX_INROW, a.y1 + ((n * F1 + fg * 4 + fl) * C + c) * (int64_t)T,
+                                        row_bytes, &bar_in_full[buf]);
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: D' -> diagonal sums -> k1[f] * partial dW1 ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+        int nu = 0;
+        uint32_t epi_phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
+            int m, fg, r_lo, r_hi;
+            unit_rows(u, m, fg, r_lo, r_hi);
+            const int sp = (u >> 1) - m * S;
+            tc::mbar_wait(&bar_accfull, nu & 1);
+            tc::tc_fence_after_sync();
+            for (int fl = 0; fl < 4; ++fl) {
+                for (int mt = 0; mt < mtiles; ++mt) {
+                    float v[32];
+                    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * 128 + fl * 32, v);
+                    tc::tmem_ld_wait();
+                    float *drow = diag + (size_t)(mt * 128 + warp * 32 + lane) * TCW_SP;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) drow[j] = v[j];
+                }
+                if (fl == 3) {
+                    tc::tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_accempty);
+                }
+                epi_sync(&bar_epi, epi_phase);
+                const int f = fg * 4 + fl;
+                const float k1 = a.params[(int64_t)m * a.pstride + a.og1 + f] * a.bnf1[(int64_t)m * F1 + f].y;
+                float *dst = a.part + (((int64_t)m * S + sp) * F1 + f) * K1;
+                for (int k = tid; k < K1; k += 128) {
+                    float acc = 0.f;
+                    const float *p = diag + (size_t)(k + DELTA) * TCW_SP;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc += p[j * (TCW_SP + 1)];
+                    dst[k] = acc * k1;
+                }
+                epi_sync(&bar_epi, epi_phase);
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 12) tc::tmem_dealloc(tmem, 512);
+}
+
+// dW2[m][g][c] = k2[g] * sum over the model's units (in order) and the four time quarters of the per-unit slots.
+__global__ void __launch_bounds__(256)
+dw2_fused_reduce_kernel(const float *__restrict__ partw2, int S, int C, const float *__restrict__ params,
+                        int64_t pstride, int64_t og2, int64_t oW2, const float4 *__restrict__ bnf2,
+                        float *__restrict__ grads) {
+    const int m = blockIdx.x, G = 64;
+    for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
+        const int gch = i / C, c = i - gch * C;
+        const int fg = gch >> 5, j = gch & 31;
+        float s = 0.f;
+        for (int sp = 0; sp < S; ++sp) {
+            const float *p = partw2 + (((int64_t)(m * S + sp) * 2 + fg) * 4) * TCX_CMAX * 32 + c * 32 + j;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) s += p[qq * TCX_CMAX * 32];
+        }
+        const float k2 = params[(int64_t)m * pstride + og2 + gch] * bnf2[(int64_t)m * G + gch].y;
+        grads[(int64_t)m * pstride + oW2 + i] = s * k2;
+    }
+}
+
+}  // namespace
+
+// shape / environment part of the decision (the workspace layout may depend on this, never on the BN mode)
+bool tconv_bwd_fused_shape_ok(const NetDims &d) {
+    if (!tconv_bwd_dw_use_tc(d)) return false;
+    if (!tc_path_enabled("EAV_FUSE_BWD")) return false;
+    return d.F1 == 8 && d.D == 8 && d.C <= TCX_CMAX;
+}
+bool tconv_bwd_fused_ok(const NetDims &d) { return !d.bn_train && tconv_bwd_fused_shape_ok(d); }
+size_t tconv_bwd_fused_partw2_floats(const NetDims &d) {
+    return (size_t)d.M * tconv_bwd_dw_tc_splits(d) * 2 * 4 * TCX_CMAX * 32;
+}
+
+int launch_tconv_bwd_fused_tc(const NetDims &d, const float *x, const int32_t *x_index, const float *dz2,
+                              const float *y1, const float4 *bnf1, const float4 *bnf2, const float *params,
+                              float *part, float *partw2, float *partbn, float *grads, int S, cudaStream_t st) {
+    const size_t smem = TCX_SMEM_FLOATS * 4;
+    static PerDevice<bool> attr_set_pd(false);
+    bool &attr_set = attr_set_pd.here();
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tconv_bwd_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        EAV_REQUIRE(e == cudaSuccess, (int)e, "tconv_bwd_fused_tc: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int sms = device_sm_count();
+    const int units = 2 * d.M * S;
+    const int grid = units < sms ? units : sms;
+    FusedBwdArgs a{dz2, y1, bnf1, bnf2, params, d.pstride, d.oW2, d.og1, d.og2, part, partw2, partbn,
+                   d.variant == EAV_VARIANT_TOR ? 1 : 0};
+    tconv_bwd_fused_tc_kernel<<<grid, TCX_THREADS, smem, st>>>(x, x_index, a, d.M, d.B, d.C, d.T, d.K1, d.pad1l, S);
+    EAV_CUDA_LAUNCH_CHECK("tconv_bwd_fused_tc");
+    dw2_fused_reduce_kernel<<<d.M, 256, 0, st>>>(partw2, S, d.C, params, d.pstride, d.og2, d.oW2, bnf2, grads);
+    EAV_CUDA_LAUNCH_CHECK("dw2_fused_reduce");
+    return 0;
+}
+
 bool tconv_bwd_dw_use_tc(const NetDims &d) {
     if (!tc_env_enabled()) return false;
     const int delta = ((d.pad1l + 3) & ~3) - d.pad1l;
