@@ -79,6 +79,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Same wait for roles that idle for a long time (an epilogue waiting ~100 us for its unit, the MMA warp waiting for the
+// next staged row): between polls the warp sleeps `ns` nanoseconds instead of spinning.  A spinning warp issues
+// ~6 instructions per poll on the same scheduler the producer warps need (ncu on tconv_bwd_fused_tc_kernel: 20 % of
+// all issued instructions were polls and the producers lost 15 % of their cycles to "not selected").
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+        if ((++spins & 0x3FFu) == 0) {
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > EAV_SPIN_TIMEOUT_NS) __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -630,7 +630,7 @@ constexpr int TCX_PROD_WARPS = 8;
 constexpr int TCX_THREADS = 16 * 32;     // 4 epilogue + 8 producer + MMA + loader warp + 2 idle warps completing the last warpgroup
 constexpr int TCX_STAGES = 5;
 constexpr int TCX_CMAX = 32;                               // electrodes the shared-memory tables hold
-constexpr int TCX_NB = 3;                                  // input row buffers (TMA prefetch depth)
+constexpr int TCX_NB = 4;                                  // input row buffers (TMA prefetch depth)
 constexpr int TCX_INROW = 512;                             // floats per staged row (x, y1 of 4 filters): 5 rows per buffer
 constexpr size_t TCX_SMEM_FLOATS = (size_t)TCX_STAGES * TCW_STAGE_FLOATS + 384 * TCW_SP + TCX_CMAX * 32 +
                                    4 * TCX_CMAX * 32 + TCX_PROD_WARPS * 4 + TCX_NB * 5 * TCX_INROW;
@@ -760,6 +760,18 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
             }
             float p1[2] = {0.f, 0.f}, p2[2] = {0.f, 0.f};
             int b = r_lo / C, c = r_lo - b * C;
+            // The cross-lane sum of a row's 16 dW2 accumulators is a chain of 5 dependent shuffles; it is issued one
+            // row late, in the same basic block as the next row's FFMA work, so its latency hides under that work.
+            float accp[16];
+            int cprev = -1;
+            auto flush_dw2 = [&]() {
+                const float tot = transpose_reduce16(accp, lane);
+                if ((lane & 1) == 0) {
+                    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    float *slot = dw2s + (q * TCX_CMAX + cprev) * 32 + fp * 16 + idx;
+                    *slot += tot;
+                }
+            };
             for (int r = r_lo; r < r_hi; ++r) {
                 const int64_t n = (int64_t)m * B + b;
                 if (n != cur_n) {                                // a new sample: its dz2 stays in registers for C rows
@@ -782,6 +794,7 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                 for (int h = 0; h < 2; ++h) yv[h] = *reinterpret_cast<const float4 *>(in + (1 + fp * 2 + h) * TCX_INROW + t);
                 float acc[16];
                 float4 outv[2];
+                if (cprev >= 0) flush_dw2();                                // previous row's dW2 sums (see above)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float4 v0 = *reinterpret_cast<const float4 *>(vtab + c * 32 + fp * 16 + h * 8);
@@ -842,15 +855,13 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bar_full[s]);
                 if (++s == TCX_STAGES) { s = 0; sfull = 1; sphase ^= 1u; }
-                // dW2 of this row: 16 (filter, depth) sums over the warp's 128 time steps -> this warp's own slot
-                const float tot = transpose_reduce16(acc, lane);
-                if ((lane & 1) == 0) {
-                    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    float *slot = dw2s + (q * TCX_CMAX + c) * 32 + fp * 16 + idx;
-                    *slot += tot;
-                }
+                // dW2 of this row: 16 (filter, depth) sums over the warp's 128 time steps, reduced during the next row
+#pragma unroll
+                for (int i = 0; i < 16; ++i) accp[i] = acc[i];
+                cprev = c;
                 if (++c == C) { c = 0; ++b; }
             }
+            if (cprev >= 0) flush_dw2();
             // ---- end of unit: dW2 slots and BatchNorm-1 sums -> global partials (fixed order)
 #pragma unroll
             for (int h = 0; h < 2; ++h) { p1[h] = warp_sum(p1[h]); p2[h] = warp_sum(p2[h]); }
@@ -881,10 +892,10 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
                 int m, fg, r_lo, r_hi;
                 unit_rows(u, m, fg, r_lo, r_hi);
-                if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);
+                if (nu > 0) tc::mbar_wait_sleep(&bar_accempty, (nu - 1) & 1, 200);
                 for (int r = r_lo; r < r_hi; ++r, ++g) {
                     const int s = g % TCX_STAGES, use = g / TCX_STAGES;
-                    tc::mbar_wait(&bar_full[s], use & 1);
+                    tc::mbar_wait_sleep(&bar_full[s], use & 1, 40);
                     tc::tc_fence_after_sync();
                     if (leader) {
                         const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
@@ -912,16 +923,16 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
         } else if (warp == 13 && lane == 0) {
             // ---------------- loader: x row + the four y1 rows of (n, c) -> input ring, TMA bulk copies ----------------
             const uint32_t row_bytes = (uint32_t)T * 4u;
-            int g = 0;
+            int buf = 0, wrapped = 0;
+            uint32_t bphase = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 int m, fg, r_lo, r_hi;
                 unit_rows(u, m, fg, r_lo, r_hi);
-                for (int r = r_lo; r < r_hi; ++r, ++g) {
-                    const int buf = g % TCX_NB, use = g / TCX_NB;
-                    const int b = r / C, c = r - b * C;
-                    const int64_t n = (int64_t)m * B + b;
-                    const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
-                    if (use > 0) tc::mbar_wait(&bar_in_empty[buf], (use - 1) & 1);
+                int b = r_lo / C, c = r_lo - b * C;
+                int64_t n = (int64_t)m * B + b;
+                int64_t xrow = x_index ? (int64_t)x_index[n] : n;        // one dependent load per SAMPLE, not per row
+                for (int r = r_lo; r < r_hi; ++r) {
+                    if (wrapped) tc::mbar_wait(&bar_in_empty[buf], bphase ^ 1u);
                     float *dst = inbuf + (size_t)buf * 5 * TCX_INROW;
                     tc::mbar_expect_tx(&bar_in_full[buf], 5u * row_bytes);
                     tc::tma_load_1d(dst, x + (xrow * C + c) * (int64_t)T, row_bytes, &bar_in_full[buf]);
@@ -929,6 +940,11 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                     for (int fl = 0; fl < 4; ++fl)
                         tc::tma_load_1d(dst + (1 + fl) * TCX_INROW, a.y1 + ((n * F1 + fg * 4 + fl) * C + c) * (int64_t)T,
                                         row_bytes, &bar_in_full[buf]);
+                    if (++buf == TCX_NB) { buf = 0; wrapped = 1; bphase ^= 1u; }
+                    if (++c == C) {
+                        c = 0; ++b; ++n;
+                        if (r + 1 < r_hi) xrow = x_index ? (int64_t)x_index[n] : n;
+                    }
                 }
             }
         }
@@ -941,7 +957,7 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
             int m, fg, r_lo, r_hi;
             unit_rows(u, m, fg, r_lo, r_hi);
             const int sp = (u >> 1) - m * S;
-            tc::mbar_wait(&bar_accfull, nu & 1);
+            tc::mbar_wait_sleep(&bar_accfull, nu & 1, 1000);
             tc::tc_fence_after_sync();
             for (int fl = 0; fl < 4; ++fl) {
                 for (int mt = 0; mt < mtiles; ++mt) {
