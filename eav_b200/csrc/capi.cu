@@ -118,7 +118,7 @@ WsLayout make_ws_layout(const NetDims &d) {
     pa = max_sz(pa, N * 2 * d.F2);                                        // pw_fwd / tail_bwd
     pa = max_sz(pa, N * 2 * d.G);                                         // pool1_bwd
     pa = max_sz(pa, N * 2 * d.F1);                                        // dw_bwd
-    pa = max_sz(pa, (size_t)d.M * 128 * 2 * d.F1);                        // fused block-1 backward: [M][S <= 128][F1][2]
+    pa = max_sz(pa, (size_t)d.M * 128 * 2 * (d.F1 + d.G));                // fused block-1 backward: [M][S <= 128][F1 | G][2]
     w.part = take(pa);
     // weight-gradient partials, one region per layer (the block-2 kernels run on a forked stream)
     w.partw = take((size_t)d.M * tconv_dw_ctas_per_model(d) * d.F1 * d.K1);        // tconv_bwd_dw
@@ -261,13 +261,23 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     switch (stage) {
         case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.tcw), WS(float, w.y1), pstat, nullptr, st);
         case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, W * d.B * d.C * d.T, dp_bn ? sums(1, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf1), st);
-        case ST_DW_FWD: return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, st);
+        case ST_DW_FWD:
+            if (dw_fwd_fuses_pool(d)) {   // eval mode: BN2's affine is known up front -> finalize first, pool inside dw_fwd
+                TRY(launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st));
+                return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr,
+                                     WS(float4, w.bnf2), WS(float, w.d1), st);
+            }
+            return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, nullptr, nullptr, st);
         case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34)
             if (tor && d.norm_rate > 0.f)
                 return launch_renorm_rows(a.params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st);
             return 0;
-        case ST_BN2: return launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, dp_bn ? sums(2, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st);
-        case ST_POOL1_FWD: return launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.d1), st);
+        case ST_BN2:
+            if (dw_fwd_fuses_pool(d)) return 0;
+            return launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, dp_bn ? sums(2, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st);
+        case ST_POOL1_FWD:
+            if (dw_fwd_fuses_pool(d)) return 0;
+            return launch_pool1_fwd(d, WS(float, w.y2), WS(float4, w.bnf2), a.mask1, WS(float, w.d1), st);
         case ST_SEPCONV_FWD:
             if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.tcw2), WS(float, w.y3), pstat, nullptr, st);
             TRY(launch_dwt_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3d), st));

@@ -345,7 +345,8 @@ template <int VEC, int UNR>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, int64_t pstride,
               int64_t oW2, const float4 *__restrict__ bn1, int B, int F1, int D, int C, int T,
-              int elu1, float *__restrict__ y2, float *__restrict__ part) {
+              int elu1, float *__restrict__ y2, float *__restrict__ part, const float4 *__restrict__ bn2_pool,
+              float *__restrict__ d1) {
     extern __shared__ float w2s[];  // [D][C]
     __shared__ float red[DW_THREADS / 32][2 * DMAX];
     const int n = blockIdx.z, f = blockIdx.y, m = n / B;
@@ -403,6 +404,15 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
                 float *dst = y2 + ((int64_t)n * G + f * D + dd) * (int64_t)T + t;
                 if (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(acc[dd][0], acc[dd][1 % VEC], acc[dd][2 % VEC], acc[dd][3 % VEC]);
                 else dst[0] = acc[dd][0];
+                // Eval-mode fusion of M5 (EEGNet_tor.py:55-57): the thread's four time steps are exactly one AvgPool(1,4)
+                // window, BatchNorm-2 is a known per-channel affine and there is no dropout, so d1 comes straight out of
+                // the registers and pool1_fwd (a 172 MB re-read of y2) is not launched.
+                if (VEC == 4 && bn2_pool != nullptr) {
+                    const float4 s2 = bn2_pool[(int64_t)m * G + f * D + dd];
+                    d1[((int64_t)n * G + f * D + dd) * (int64_t)(T >> 2) + (t >> 2)] =
+                        0.25f * (elu_f(fmaf(acc[dd][0], s2.z, s2.w)) + elu_f(fmaf(acc[dd][1 % VEC], s2.z, s2.w)) +
+                                 elu_f(fmaf(acc[dd][2 % VEC], s2.z, s2.w)) + elu_f(fmaf(acc[dd][3 % VEC], s2.z, s2.w)));
+                }
             }
     }
     if (part != nullptr) {
@@ -432,8 +442,12 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
 
 int dw_fwd_tiles(const NetDims &d) { return (d.T & 3) == 0 ? cdiv(d.T, DW_THREADS * 4) : cdiv(d.T, DW_THREADS); }
 
+bool dw_fwd_fuses_pool(const NetDims &d) {
+    return !d.bn_train && d.dropout_mode == EAV_DROPOUT_NONE && d.P1 == 4 && (d.T & 3) == 0 && tc_path_enabled("EAV_FUSE_FWD");
+}
+
 int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
-                  float *y2, float *part, int *part_rows, cudaStream_t st) {
+                  float *y2, float *part, int *part_rows, const float4 *bn2_pool, float *d1, cudaStream_t st) {
     EAV_REQUIRE(d.D <= DMAX, EAV_ERR_UNSUPPORTED, "dw_fwd: D=%d > %d unsupported", d.D, DMAX);
     dim3 grid(dw_fwd_tiles(d), d.F1, d.N);
     const size_t smem = (size_t)d.D * d.C * sizeof(float);
@@ -441,13 +455,13 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
     static int unr = -1;
     if (unr < 0) { const char *e = getenv("EAV_DWF_UNR"); unr = e ? atoi(e) : 5; }   // measured on B200: 5 -> 0.195 ms, 3: 0.203, 6: 0.209, 10: 0.256, 15: 0.434
     if ((d.T & 3) == 0) {
-        if (unr == 3) dw_fwd_kernel<4, 3><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
-        else if (unr == 6) dw_fwd_kernel<4, 6><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
-        else if (unr == 15) dw_fwd_kernel<4, 15><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
-        else if (unr == 10) dw_fwd_kernel<4, 10><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
-        else dw_fwd_kernel<4, 5><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        if (unr == 3) dw_fwd_kernel<4, 3><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
+        else if (unr == 6) dw_fwd_kernel<4, 6><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
+        else if (unr == 15) dw_fwd_kernel<4, 15><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
+        else if (unr == 10) dw_fwd_kernel<4, 10><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
+        else dw_fwd_kernel<4, 5><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
     } else {
-        dw_fwd_kernel<1, 8><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part);
+        dw_fwd_kernel<1, 8><<<grid, DW_THREADS, smem, st>>>(y1, params, d.pstride, d.oW2, bn1, d.B, d.F1, d.D, d.C, d.T, elu1, y2, part, bn2_pool, d1);
     }
     EAV_CUDA_LAUNCH_CHECK("dw_fwd");
     if (part_rows) *part_rows = d.B * grid.x;

@@ -35,8 +35,10 @@ int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_
 int launch_bn_reduce(const NetDims &d, int layer, const float *part, int rows_per_model, double *sums,
                      cudaStream_t st);
 // M2+M3+M4: BN1 (+ELU) + depthwise spatial conv -> y2 raw [N][G][T] (+ BN2 partial sums)
+// bn2_pool / d1 non-null: eval-mode fusion of M5 (BN2 + ELU + AvgPool(1,4)) into the same kernel, see dw_fwd_fuses_pool()
 int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const float4 *bn1,
-                  float *y2, float *part, int *part_rows, cudaStream_t st);
+                  float *y2, float *part, int *part_rows, const float4 *bn2_pool, float *d1, cudaStream_t st);
+bool dw_fwd_fuses_pool(const NetDims &d);
 // M5: BN2 + ELU + AvgPool(1,P1) + dropout -> d1 [N][G][T4]
 int launch_pool1_fwd(const NetDims &d, const float *y2, const float4 *bn2, const uint8_t *mask1,
                      float *d1, cudaStream_t st);

@@ -146,9 +146,13 @@ struct FirSteps<DOWN, NTAPS, SKIP, LEAD, NQ, NQ> {
 template <typename TIn, int DOWN, int NTAPS, bool SKIP>
 __global__ void __launch_bounds__(FIR_THREADS)
 fir_decimate_kernel(const TIn *__restrict__ raw, const __grid_constant__ FirTaps taps, int n_trials, int n_chans,
-                    int trial_len, int64_t n_dec, int tile_out, int use_tma, float *__restrict__ dec) {
+                    int trial_len, int64_t n_dec, int tile_out, int use_tma, float *__restrict__ dec,
+                    const uint8_t *__restrict__ needed) {
     extern __shared__ __align__(128) float xs[];
     __shared__ __align__(8) uint64_t bar;
+    // tile == trial (TMA path): trials whose decimated samples nobody reads -- neither kept by
+    // segment_and_select_classes nor the warm-up predecessor of a kept trial -- are not computed at all
+    if (needed != nullptr && !needed[(int64_t)blockIdx.z * n_trials + blockIdx.x]) return;
     constexpr int H = (NTAPS - 1) / 2;
     constexpr int LEAD = 2;
     constexpr int WIN = DOWN * (FIR_R - 1) + NTAPS + LEAD;     // window per thread (138)
@@ -258,13 +262,20 @@ __global__ void __launch_bounds__(SOS_THREADS)
 sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, int n_chans, int n_trials,
            int chunk_len, int64_t n_dec, const int32_t *__restrict__ kept_trial, int n_kept,
            double *__restrict__ zstate, const double *__restrict__ start, int n_sub, int ep_len,
-           int n_epochs_out, float *__restrict__ epochs, int64_t n_work, int raw_layout) {
+           int n_epochs_out, float *__restrict__ epochs, int64_t n_work, int raw_layout, int warm = 0) {
+    // warm = 1 (APPLY, start == nullptr): instead of a carried start state the thread first runs the cascade from
+    // rest over the PREVIOUS trial's chunk (state only, nothing written) and then filters its own chunk.  The
+    // cascade forgets: the zero-input response over one chunk, ||A^L||, is checked on the host to be < 1e-6, so the
+    // state after the warm-up equals the true carried state to that relative accuracy (measured 1.2e-8 of the
+    // channel RMS for band [0.5, 45]; the parity gate is 1e-5).  One kernel replaces the zero-state pass over ALL
+    // trials, the carry scan and the apply pass, and trials that are neither kept nor a predecessor are never read.
     // raw_layout = 1 (legacy order, band-pass BEFORE decimation): `dec` is the raw recording
     // [S][trial][ch][chunk_len], every trial is filtered (kept_trial == nullptr: identity) and the output row
     // goes to the same position of `epochs` (= the filtered recording, n_sub = 1, ep_len = chunk_len).
     __shared__ float tile[SOS_THREADS][SOS_TILE + 1];
     __shared__ int64_t row_src[SOS_THREADS];   // offset of the chunk in dec, or -1
     __shared__ int64_t row_dst[SOS_THREADS];   // offset of the trial's first epoch row in epochs
+    __shared__ int64_t row_prev[SOS_THREADS];  // warm mode: offset of the previous trial's chunk, or -1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t w = (int64_t)blockIdx.x * SOS_THREADS + tid;
     // work item -> (sequence, trial)
@@ -284,9 +295,11 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
     if (raw_layout) {
         const int64_t subj = my_seq / n_chans, ch = my_seq - subj * n_chans;
         row_src[tid] = my_ok ? ((subj * n_trials + my_trial) * n_chans + ch) * (int64_t)chunk_len : -1;
+        row_prev[tid] = -1;
         if (APPLY) row_dst[tid] = row_src[tid];
     } else {
         row_src[tid] = my_ok ? my_seq * n_dec + (int64_t)my_trial * chunk_len : -1;
+        row_prev[tid] = (my_ok && my_trial > 0) ? my_seq * n_dec + (int64_t)(my_trial - 1) * chunk_len : -1;
         if (APPLY) {
             int64_t subj = my_seq / n_chans, ch = my_seq - subj * n_chans;
             row_dst[tid] = ((subj * n_epochs_out + (int64_t)my_slot * n_sub) * n_chans + ch) * ep_len;
@@ -296,7 +309,7 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
     double s0[NSEC], s1[NSEC];
 #pragma unroll
     for (int k = 0; k < NSEC; ++k) { s0[k] = 0.0; s1[k] = 0.0; }
-    if (APPLY && my_ok) {
+    if (APPLY && my_ok && start != nullptr) {
         const double *st = start + (my_seq * n_trials + my_trial) * (2 * NSEC);
 #pragma unroll
         for (int k = 0; k < NSEC; ++k) { s0[k] = st[2 * k]; s1[k] = st[2 * k + 1]; }
@@ -308,11 +321,14 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
     // (32 independent 128-byte row reads per warp in flight) while the current tile is being
     // filtered out of shared memory.
     float pre[32];
+    for (int pass = (APPLY && warm) ? 0 : 1; pass < 2; ++pass) {
+    const bool emit = APPLY && pass == 1;
+    const int64_t *rows = pass == 0 ? row_prev : row_src;
     auto fetch = [&](int i0) {
         const int nt = min(SOS_TILE, chunk_len - i0);
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
-            const int64_t src = row_src[warp * 32 + r];
+            const int64_t src = rows[warp * 32 + r];
             pre[r] = (src >= 0 && lane < nt) ? dec[src + i0 + lane] : 0.f;
         }
     };
@@ -335,10 +351,10 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
                     s1[k] = fma(co.b2[k], x, -co.a2[k] * y);
                     x = y;
                 }
-                if (APPLY) tile[tid][i] = (float)x;
+                if (emit) tile[tid][i] = (float)x;
             }
         }
-        if (APPLY) {
+        if (emit) {
             __syncwarp();
             const int i = i0 + lane;
             const int q = i / ep_len, off = i - q * ep_len;
@@ -349,6 +365,7 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
                     epochs[row_dst[row] + q * ep_stride + off] = tile[row][lane];
             }
         }
+    }
     }
     if (!APPLY && my_ok) {
         double *z = zstate + (my_seq * n_trials + my_trial) * (2 * NSEC);
@@ -472,6 +489,19 @@ __global__ void invert_slots_kernel(const int32_t *__restrict__ epoch_slot, int 
     if (slot >= 0 && slot < n_kept) kept_trial[(int64_t)subj * n_kept + slot] = trial;
 }
 
+// needed[s][trial] = 1 for kept trials and for the trial before a kept one (its chunk warms the filter state up)
+__global__ void needed_trials_kernel(const int32_t *__restrict__ epoch_slot, int n_trials, int n_kept, int total,
+                                     uint8_t *__restrict__ needed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int trial = i % n_trials;
+    const int slot = epoch_slot[i];
+    const bool kept = slot >= 0 && slot < n_kept;
+    bool next_kept = false;
+    if (trial + 1 < n_trials) { const int sn = epoch_slot[i + 1]; next_kept = sn >= 0 && sn < n_kept; }
+    needed[i] = (kept || next_kept) ? 1 : 0;
+}
+
 // helper stream for overlapping the fp64 SOS passes with the next group's FIR (one per device)
 struct PreSide { cudaStream_t stream; cudaEvent_t fork[4], join; };
 static PreSide *pre_side_stream() {
@@ -488,7 +518,7 @@ static PreSide *pre_side_stream() {
     return &pool[dev];
 }
 
-struct PreLayout { size_t dec, z, start, kept, gtab, filt, total; };
+struct PreLayout { size_t dec, z, start, kept, gtab, filt, needed, total; };
 static PreLayout pre_layout(const eav_preproc_cfg *c, bool own_dec) {
     PreLayout l;
     size_t o = 0;
@@ -503,6 +533,7 @@ static PreLayout pre_layout(const eav_preproc_cfg *c, bool own_dec) {
     // legacy order: the band-passed recording at fs_orig (fp32, raw layout)
     l.filt = take(c->order == EAV_PREPROC_ORDER_BANDPASS_FIRST
                       ? (size_t)c->n_subjects * c->n_trials * c->n_chans * c->trial_len * sizeof(float) : 0);
+    l.needed = take((size_t)c->n_subjects * c->n_trials);
     l.total = o;
     return l;
 }
@@ -598,7 +629,8 @@ __global__ void epoch_gather_kernel(const float *__restrict__ dec, const int32_t
 }
 
 template <typename TIn, bool SKIP>
-static int launch_fir_5_101(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, float *dec, cudaStream_t st) {
+static int launch_fir_5_101(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, float *dec,
+                            const uint8_t *needed, cudaStream_t st) {
     const int chunk = c->trial_len / c->down;
     const int64_t n_dec = (int64_t)c->n_trials * chunk;
     const int tile_out = chunk <= FIR_OT ? chunk : FIR_OT;
@@ -616,18 +648,18 @@ static int launch_fir_5_101(const eav_preproc_cfg *c, const TIn *raw, const FirT
         attr_set = true;
     }
     fir_decimate_kernel<TIn, 5, 101, SKIP><<<dim3(tiles, c->n_chans, c->n_subjects), FIR_THREADS, smem, st>>>(
-        raw, taps, c->n_trials, c->n_chans, c->trial_len, n_dec, tile_out, use_tma, dec);
+        raw, taps, c->n_trials, c->n_chans, c->trial_len, n_dec, tile_out, use_tma, dec, use_tma ? needed : nullptr);
     return 0;
 }
 
 template <typename TIn>
 static int run_fir(const eav_preproc_cfg *c, const TIn *raw, const FirTaps &taps, bool skip_zero_taps, float *dec,
-                   cudaStream_t st) {
+                   cudaStream_t st, const uint8_t *needed = nullptr) {
     const int chunk = c->trial_len / c->down;
     const int64_t n_dec = (int64_t)c->n_trials * chunk;
     if (c->down == 5 && c->n_taps == 101) {
-        if (skip_zero_taps) launch_fir_5_101<TIn, true>(c, raw, taps, dec, st);
-        else launch_fir_5_101<TIn, false>(c, raw, taps, dec, st);
+        if (skip_zero_taps) launch_fir_5_101<TIn, true>(c, raw, taps, dec, needed, st);
+        else launch_fir_5_101<TIn, false>(c, raw, taps, dec, needed, st);
     } else {
         fir_decimate_generic_kernel<TIn><<<dim3((unsigned)cdiv64(n_dec, FIR_THREADS), c->n_chans, c->n_subjects),
                                           FIR_THREADS, 0, st>>>(raw, taps, c->n_taps, c->down, c->n_trials,
@@ -793,6 +825,77 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
             EAV_CUDA_LAUNCH_CHECK("epoch_gather");
         }
         return 0;
+    }
+    // Forgetting-filter fast path (the default whenever it is valid): if the cascade's zero-input response over one
+    // chunk is negligible (||A^L||_inf < 1e-6: 2.9e-7 for the band [0.5, 45] of the callers, 1e-15 for [1, 40], but
+    // 1e-3 for [0.3, 49], which therefore takes the exact path below), a trial's start state is the end state of a
+    // from-rest run over the previous trial alone.  Then only kept trials and their predecessors are decimated, and ONE
+    // SOS kernel (warm-up over the previous chunk + apply) replaces state pass, carry scan and apply pass.
+    // EAV_SOS_EXACT=1 forces the exact chunked scan.
+    {
+        double ninf = 0.0;
+        for (int i = 0; i < NS; ++i) {
+            double rsum = 0.0;
+            for (int j = 0; j < NS; ++j) rsum += fabs(A.a[i * NS + j]);
+            if (rsum > ninf) ninf = rsum;
+        }
+        const char *ex = getenv("EAV_SOS_EXACT");
+        const bool exact = ex && ex[0] == '1';
+        if (!exact && ninf < 1e-6 && dec_out == nullptr && n_kept > 0) {
+            uint8_t *needed = reinterpret_cast<uint8_t *>(ws + l.needed);
+            needed_trials_kernel<<<cdiv(total, 256), 256, 0, st>>>(epoch_slot, cfg->n_trials, n_kept, total, needed);
+            EAV_CUDA_LAUNCH_CHECK("needed_trials");
+            // Subject groups: the fp64-bound SOS kernel of group i runs on a forked stream while the HBM-bound FIR of
+            // group i+1 runs on the caller's stream (EAV_PREPROC_GROUPS, default 1).
+            int ng = 1;
+            { const char *e = getenv("EAV_PREPROC_GROUPS"); if (e && atoi(e) > 0) ng = atoi(e); }
+            if (ng > cfg->n_subjects) ng = cfg->n_subjects;
+            PreSide *sd = ng > 1 ? pre_side_stream() : nullptr;
+            if (sd == nullptr) ng = 1;
+            const size_t raw_subj_e = (size_t)cfg->n_trials * cfg->n_chans * cfg->trial_len;
+            const size_t dec_subj_e = (size_t)cfg->n_chans * cfg->n_trials * chunk;
+            const size_t ep_subj_e = (size_t)n_epochs_out * cfg->n_chans * (chunk / cfg->n_sub);
+            const int64_t n_dec = (int64_t)cfg->n_trials * chunk;
+            for (int g = 0; g < ng; ++g) {
+                const int s0 = (int)((int64_t)cfg->n_subjects * g / ng), s1 = (int)((int64_t)cfg->n_subjects * (g + 1) / ng);
+                if (s1 <= s0) continue;
+                eav_preproc_cfg sub = *cfg;
+                sub.n_subjects = s1 - s0;
+                float *dec_g = dec + s0 * dec_subj_e;
+                const uint8_t *need_g = needed + (size_t)s0 * cfg->n_trials;
+                if (cfg->raw_is_f64) rc = run_fir<double>(&sub, reinterpret_cast<const double *>(raw) + s0 * raw_subj_e, ft, skip_zero, dec_g, st, need_g);
+                else rc = run_fir<float>(&sub, reinterpret_cast<const float *>(raw) + s0 * raw_subj_e, ft, skip_zero, dec_g, st, need_g);
+                if (rc) return rc;
+                cudaStream_t sst = st;
+                if (sd != nullptr) {
+                    cudaEventRecord(sd->fork[g % 4], st);
+                    cudaStreamWaitEvent(sd->stream, sd->fork[g % 4], 0);
+                    sst = sd->stream;
+                }
+                const int64_t work = (int64_t)sub.n_subjects * cfg->n_chans * n_kept;
+                const int32_t *kept_g = kept + (size_t)s0 * n_kept;
+                float *ep_g = epochs + s0 * ep_subj_e;
+#define EAV_WARM(NS_)                                                                                               \
+    sos_kernel<NS_, true><<<(unsigned)cdiv64(work, SOS_THREADS), SOS_THREADS, 0, sst>>>(                            \
+        dec_g, co, cfg->n_chans, cfg->n_trials, chunk, n_dec, kept_g, n_kept, nullptr, nullptr, cfg->n_sub,         \
+        chunk / cfg->n_sub, n_epochs_out, ep_g, work, 0, 1)
+                switch (NSEC) {
+                    case 1: EAV_WARM(1); break;
+                    case 2: EAV_WARM(2); break;
+                    case 3: EAV_WARM(3); break;
+                    case 4: EAV_WARM(4); break;
+                    case 5: EAV_WARM(5); break;
+                    default: EAV_WARM(6); break;
+                }
+#undef EAV_WARM
+                EAV_CUDA_LAUNCH_CHECK("sos_warm_apply");
+            }
+            if (sd != nullptr) {
+                cudaEventRecord(sd->join, sd->stream);
+                cudaStreamWaitEvent(st, sd->join, 0);
+            }
+            return 0;
+        }
     }
     // Optional grouping (EAV_PREPROC_GROUPS=n): the FIR of group i+1 on the caller's stream, the SOS
     // passes of group i on a forked stream.  The idea was to overlap the fp32/HBM-bound FIR with the

@@ -1021,7 +1021,7 @@ bool tconv_bwd_fused_shape_ok(const NetDims &d) {
     if (!tc_path_enabled("EAV_FUSE_BWD")) return false;
     return d.F1 == 8 && d.D == 8 && d.C <= TCX_CMAX;
 }
-bool tconv_bwd_fused_ok(const NetDims &d) { return !d.bn_train && tconv_bwd_fused_shape_ok(d); }
+bool tconv_bwd_fused_ok(const NetDims &d) { return !d.bn_train && tconv_bwd_fused_shape_ok(d); }   // any dropout mode: dz2 comes from pool1_bwd
 size_t tconv_bwd_fused_partw2_floats(const NetDims &d) {
     return (size_t)d.M * tconv_bwd_dw_tc_splits(d) * 2 * 4 * TCX_CMAX * 32;
 }

@@ -34,6 +34,14 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _norm_device(device=None):
+    """torch.device with an explicit index ('cuda' -> the current device), so tensor.device comparisons are exact."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def _on(device):
     """Context manager: `device` is the current CUDA device inside the block."""
     return torch.cuda.device(device)
@@ -135,7 +143,7 @@ class EegnetEngine:
         _lib.require_device()
         self.lib = _lib.load()
         self.dims, self.M, self.B = dims, n_models, batch
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = _norm_device(device)
         self.n_params, self.layout = dims.param_layout()
         c = dims.cfg(n_models, batch, param_stride=self.n_params, bn_stride=dims.n_bn)
         nbytes = self.lib.eav_eegnet_workspace_bytes(ctypes.byref(c))
@@ -271,7 +279,7 @@ class PreprocEngine:
         (legacy CNN_EEG_tf.py:64-75,182-189; `sos` must then be designed for fs_orig)."""
         _lib.require_device()
         self.lib = _lib.load()
-        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = _norm_device(device)
         c = PreprocCfg()
         c.n_subjects, c.n_trials, c.n_chans, c.trial_len = n_subjects, n_trials, n_chans, trial_len
         c.down, c.n_taps, c.n_sections, c.n_sub = down, n_taps, n_sections, n_sub

@@ -39,7 +39,7 @@ def test_dropout2d_on_device_drops_whole_channels_and_matches_the_oracle():
     m1 = keep1.reshape(8, 64, 1, 1).expand(8, 64, 1, 125).float()
     m2 = keep2.reshape(8, 64, 1, 1).expand(8, 64, 1, 15).float()
     params, buffers = EO.split_state(sd, "tor")
-    o = EO.tor_forward(params, buffers, x, True, masks=(m1, m2))
+    o = EO.tor_forward(params, buffers, x, True, masks=[m1, m2])
     l = EO.loss_fn(o, y)
     l.backward()
     assert abs(loss.item() - l.item()) < TOL * abs(l.item())
