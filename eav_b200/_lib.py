@@ -32,6 +32,12 @@ class EegnetCfg(Structure):
                 + [("dp_world", c_int32), ("reserved", c_int32)])
 
 
+class ShallowCfg(Structure):
+    _fields_ = ([(n, c_int32) for n in ("batch", "chans", "samples", "n_filters", "kern", "n_layers", "ffn", "pool",
+                                        "stride", "n_classes", "bn_train", "dropout_mode")]
+                + [(n, c_float) for n in ("dropout_p", "bn_eps", "bn_momentum", "ln_eps")])
+
+
 # every symbol include/eav_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "eav_last_error_string": (c_char_p, []),
@@ -65,6 +71,12 @@ SYMBOLS = {
     "eav_epoch_accumulate": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "eav_epoch_commit": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
                                  c_void_p]),
+    "eav_shallow_param_layout": (c_int64, [POINTER(ShallowCfg), POINTER(c_int64), POINTER(c_int64)]),
+    "eav_shallow_workspace_bytes": (c_size_t, [POINTER(ShallowCfg)]),
+    "eav_shallow_forward": (c_int, [POINTER(ShallowCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
+    "eav_shallow_backward": (c_int, [POINTER(ShallowCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_size_t, c_void_p]),
     "eav_renorm_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libeav_b200.so")
-SOURCES = ["capi.cu", "eegnet_fwd.cu", "eegnet_bwd.cu", "optim.cu", "preproc.cu", "tconv_tc.cu", "sepconv_tc.cu", "peer_reduce.cu", "epoch.cu"]
+SOURCES = ["capi.cu", "eegnet_fwd.cu", "eegnet_bwd.cu", "optim.cu", "preproc.cu", "tconv_tc.cu", "sepconv_tc.cu", "peer_reduce.cu", "epoch.cu", "shallow.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -272,6 +272,43 @@ int eav_epoch_commit(double *train_acc, double *val_acc, int32_t n_models, int32
                      int32_t n_val_steps, int32_t n_val, float *history, int32_t max_epochs,
                      int64_t *epoch_dev, void *stream);
 
+/* ------------------------------------------------------------------------- */
+/* ShallowConvNet of Transformer_torch/Transformer_EEG.py:107-148: Conv2d(1,40,(1,13)) -> 40
+ * per-filter spatial Linear(30,1) -> n_layers single-head transformer layers (d = n_filters) -> BatchNorm2d ->
+ * square -> AvgPool((1,pool), stride) -> log(clamp(., 1e-7, 1e4)) -> dropout -> Linear(F*U, n_classes, bias=False)
+ * -> softmax.  One model, any batch; fp32.                                   */
+/* ------------------------------------------------------------------------- */
+typedef struct eav_shallow_cfg {
+    int32_t batch, chans, samples;     /* B, 30, 500                                          */
+    int32_t n_filters, kern;           /* 40 temporal filters of 13 taps (no padding)         */
+    int32_t n_layers, ffn;             /* 12 transformer layers, hidden width 160             */
+    int32_t pool, stride;              /* AvgPool window 35, stride 7                         */
+    int32_t n_classes;
+    int32_t bn_train;                  /* 1: batch statistics + running-stat update           */
+    int32_t dropout_mode;              /* 0: none (eval); 1: caller supplies keep-masks       */
+    float   dropout_p, bn_eps, bn_momentum, ln_eps;
+} eav_shallow_cfg;
+
+/* Parameters live in ONE flat fp32 array in the reference's named_parameters() order: conv.weight, bn.weight,
+ * bn.bias, embedding.value_proj.{0..F-1}.weight, then per layer W_q W_k W_v ffn.net.0.{weight,bias}
+ * ffn.net.3.{weight,bias} norm1.{weight,bias} norm2.{weight,bias}, then fc.weight.  offsets14 receives the offsets
+ * of  conv bn.w bn.b emb | (layer 0) Wqkv W1 b1 W2 b2 g1 be1 g2 be2 | fc;  layer l adds l * *layer_stride.
+ * Returns the parameter count. */
+int64_t eav_shallow_param_layout(const eav_shallow_cfg *cfg, int64_t *offsets14, int64_t *layer_stride);
+size_t eav_shallow_workspace_bytes(const eav_shallow_cfg *cfg);
+/*
+ * x        device [B][chans][samples] f32
+ * bn_state device [2][n_filters] f32: running_mean, running_var (updated when bn_train)
+ * masks    device u8 keep flags in forward call order (dropout_mode 1), else NULL:
+ *          per layer  [B*T'][F] (after norm1), [B*T'][ffn] (inside the FFN), [B*T'][F] (after norm2);  then [B][F*U]
+ * out      device [B][n_classes] probabilities;  workspace keeps the activations for eav_shallow_backward.
+ */
+int eav_shallow_forward(const eav_shallow_cfg *cfg, const float *x, const float *params, float *bn_state,
+                        const uint8_t *masks, float *out, void *workspace, size_t workspace_bytes, void *stream);
+/* Gradient of every parameter (grads: same layout as params, overwritten) given d(loss)/d(out). */
+int eav_shallow_backward(const eav_shallow_cfg *cfg, const float *x, const float *params, const float *dout,
+                         const uint8_t *masks, float *grads, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Measured-peak helper for bench.py: runs a register-resident FFMA loop on every SM
  * and returns the achieved fp32 TFLOP/s (host-synchronous; not part of the hot path). */
 int eav_measure_fp32_peak(double *tflops, void *stream);
