@@ -77,6 +77,7 @@ SYMBOLS = {
                                     c_size_t, c_void_p]),
     "eav_shallow_backward": (c_int, [POINTER(ShallowCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_size_t, c_void_p]),
+    "eav_epoch_commit_val": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
     "eav_renorm_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "eav_measure_fp32_peak": (c_int, [POINTER(c_double), c_void_p]),
     "eav_measure_fp32_peak_outer": (c_int, [POINTER(c_double), c_void_p]),

@@ -56,14 +56,31 @@ __global__ void epoch_commit_kernel(double *__restrict__ train_acc, double *__re
     if (m < M) {
         float *h = history + ((e % max_epochs) * (long long)M + m) * 3;
         h[0] = n_train_steps > 0 ? (float)(train_acc[2 * m] / n_train_steps) : 0.f;
-        h[1] = n_val_steps > 0 ? (float)(val_acc[2 * m] / n_val_steps) : 0.f;
-        h[2] = n_val > 0 ? (float)(val_acc[2 * m + 1] / n_val) : 0.f;
         train_acc[2 * m] = train_acc[2 * m + 1] = 0.0;
-        val_acc[2 * m] = val_acc[2 * m + 1] = 0.0;
+        if (val_acc != nullptr) {
+            h[1] = n_val_steps > 0 ? (float)(val_acc[2 * m] / n_val_steps) : 0.f;
+            h[2] = n_val > 0 ? (float)(val_acc[2 * m + 1] / n_val) : 0.f;
+            val_acc[2 * m] = val_acc[2 * m + 1] = 0.0;
+        }
     }
     // every thread has read the counter before any thread of this (single-CTA) launch bumps it
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0) *epoch_dev = e + 1;
+}
+
+// validation results of epoch (*epoch_dev + epoch_offset), committed one graph later than its training loss when the
+// validation pass is pipelined with the next epoch's training (trainer_core.EpochRunner)
+__global__ void epoch_commit_val_kernel(double *__restrict__ val_acc, int M, int n_val_steps, int n_val,
+                                        float *__restrict__ history, int max_epochs, const long long *__restrict__ epoch_dev,
+                                        int epoch_offset) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    long long e = *epoch_dev + epoch_offset;
+    if (e < 0) e = 0;
+    float *h = history + ((e % max_epochs) * (long long)M + m) * 3;
+    h[1] = n_val_steps > 0 ? (float)(val_acc[2 * m] / n_val_steps) : 0.f;
+    h[2] = n_val > 0 ? (float)(val_acc[2 * m + 1] / n_val) : 0.f;
+    val_acc[2 * m] = val_acc[2 * m + 1] = 0.0;
 }
 
 }  // namespace eav
@@ -98,12 +115,22 @@ extern "C" int eav_epoch_accumulate(const float *loss, const int32_t *n_correct,
 extern "C" int eav_epoch_commit(double *train_acc, double *val_acc, int32_t n_models, int32_t n_train_steps,
                                 int32_t n_val_steps, int32_t n_val, float *history, int32_t max_epochs,
                                 int64_t *epoch_dev, void *stream) {
-    EAV_REQUIRE(train_acc && val_acc && history && epoch_dev, EAV_ERR_BAD_ARG, "epoch_commit: null pointer");
+    EAV_REQUIRE(train_acc && history && epoch_dev, EAV_ERR_BAD_ARG, "epoch_commit: null pointer");
     EAV_REQUIRE(n_models > 0 && n_models <= 1024 && max_epochs > 0, EAV_ERR_BAD_ARG,
                 "epoch_commit: n_models=%d (<= 1024) max_epochs=%d", n_models, max_epochs);
     epoch_commit_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(train_acc, val_acc, n_models, n_train_steps, n_val_steps,
                                                              n_val, history, max_epochs,
                                                              reinterpret_cast<long long *>(epoch_dev));
     EAV_CUDA_LAUNCH_CHECK("epoch_commit");
+    return 0;
+}
+
+extern "C" int eav_epoch_commit_val(double *val_acc, int32_t n_models, int32_t n_val_steps, int32_t n_val, float *history,
+                                    int32_t max_epochs, const int64_t *epoch_dev, int32_t epoch_offset, void *stream) {
+    EAV_REQUIRE(val_acc && history && epoch_dev, EAV_ERR_BAD_ARG, "epoch_commit_val: null pointer");
+    EAV_REQUIRE(n_models > 0 && max_epochs > 0, EAV_ERR_BAD_ARG, "epoch_commit_val: n_models=%d max_epochs=%d", n_models, max_epochs);
+    epoch_commit_val_kernel<<<cdiv(n_models, 128), 128, 0, (cudaStream_t)stream>>>(
+        val_acc, n_models, n_val_steps, n_val, history, max_epochs, reinterpret_cast<const long long *>(epoch_dev), epoch_offset);
+    EAV_CUDA_LAUNCH_CHECK("epoch_commit_val");
     return 0;
 }

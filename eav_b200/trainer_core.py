@@ -39,6 +39,7 @@ class _Program:
         self.use_x_index = True
         self.x_src = None            # alternative data source (host-fed staging buffer)
         self.y_src = None
+        self.params = self.bn_state = self.workspace = None   # optional overrides (validation on a parameter snapshot)
 
     def cfg(self):
         c = self.core
@@ -64,8 +65,11 @@ class _Program:
         y = self.y_src if self.y_src is not None else c.y
         idx = self.idx if self.use_x_index else None
         st = _stream()
-        _lib.check(lib.eav_eegnet_forward(ctypes.byref(cfg), _ptr(x), _ptr(idx), _ptr(c.params), _ptr(c.bn_state),
-                                          _ptr(self.mask1), _ptr(self.mask2), _ptr(self.out), _ptr(c.workspace),
+        params = self.params if self.params is not None else c.params
+        bn_state = self.bn_state if self.bn_state is not None else c.bn_state
+        workspace = self.workspace if self.workspace is not None else c.workspace
+        _lib.check(lib.eav_eegnet_forward(ctypes.byref(cfg), _ptr(x), _ptr(idx), _ptr(params), _ptr(bn_state),
+                                          _ptr(self.mask1), _ptr(self.mask2), _ptr(self.out), _ptr(workspace),
                                           c.ws_bytes, st), "eav_eegnet_forward")
         _lib.check(lib.eav_eegnet_loss(ctypes.byref(cfg), _ptr(self.out), _ptr(y), _ptr(idx), _ptr(self.loss),
                                        _ptr(self.dout), _ptr(self.ncorrect), st), "eav_eegnet_loss")
@@ -241,10 +245,10 @@ class SubjectBatchTrainer:
         return p.loss, p.ncorrect, p.out
 
     def epoch_runner(self, n_train, n_test, batch, rows_per_model=None, train_first_row=0, test_first_row=None,
-                     subject_ids=None, max_epochs=1024, seed=None):
+                     subject_ids=None, max_epochs=1024, seed=None, pipeline_validation=True):
         """Whole-epoch CUDA graphs over this trainer's resident rows (see EpochRunner)."""
         return EpochRunner(self, n_train, n_test, batch, rows_per_model, train_first_row, test_first_row,
-                           subject_ids, max_epochs, seed)
+                           subject_ids, max_epochs, seed, pipeline_validation)
 
     # -------------------------------------------------------- host-fed steps (end-to-end path)
     def host_step_program(self, B, bn_train=True, kind="train", x_src=None, y_src=None, slot=0):
@@ -275,12 +279,18 @@ class EpochRunner:
 
     Row layout of core.x / core.y: model m's training rows are train_first_row + m*rows_per_model
     + [0, n_train), its test rows test_first_row + m*rows_per_model + [0, n_test).
-    Two graphs exist at most: train-mode BN + dropout (the reference's epoch 1) and
-    eval-mode BN (every later epoch).
+    Graphs: train-mode BN + dropout (the reference's epoch 1) and eval-mode BN (every later
+    epoch), each with and without a validation branch.
+
+    pipeline_validation (default): the validation pass of epoch e runs on a SNAPSHOT of the parameters
+    taken at the end of epoch e, as a parallel branch of the graph that trains epoch e+1 -- the same
+    numbers as validating in between (the snapshot is what validate() would have seen), but the forward-only
+    validation kernels fill the SMs the small training kernels leave idle (5-6 models per GPU when the 42
+    subjects are spread over 8 GPUs).  results() / finish() run the last epoch's validation.
     """
 
     def __init__(self, core, n_train, n_test, batch, rows_per_model=None, train_first_row=0, test_first_row=None,
-                 subject_ids=None, max_epochs=1024, seed=None):
+                 subject_ids=None, max_epochs=1024, seed=None, pipeline_validation=True):
         self.core, self.n_train, self.n_test, self.batch = core, int(n_train), int(n_test), int(batch)
         self.rows_per_model = int(rows_per_model if rows_per_model is not None else n_train + n_test)
         self.train_first_row = int(train_first_row)
@@ -307,6 +317,12 @@ class EpochRunner:
         self.val_acc = torch.zeros(M, 2, dtype=torch.float64, device=dev)
         self.history = torch.zeros(self.max_epochs, M, 3, dtype=torch.float32, device=dev)
         self._graphs = {}
+        self.pipeline = bool(pipeline_validation) and len(self.val_sizes) > 0
+        self._val_pending = False
+        if self.pipeline:
+            self.params_val, self.bn_val = core.params.clone(), core.bn_state.clone()
+            self.ws_val = torch.empty(core.ws_bytes, dtype=torch.uint8, device=dev)
+            self._val_stream = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------------------
     def step_index(self, s):
@@ -335,12 +351,12 @@ class EpochRunner:
         M = self.core.M
         return [tmp[s, :M * Bs].cpu() for s, Bs in enumerate(self.train_sizes)]
 
-    def enqueue(self, bn_train):
+    def enqueue(self, bn_train, with_val=False):
         """Issue one whole epoch on the current stream (kernel launches only: capturable)."""
         with _on(self.core.device):
-            self._enqueue(bn_train)
+            self._enqueue(bn_train, with_val)
 
-    def _enqueue(self, bn_train):
+    def _enqueue_train(self, bn_train):
         c, lib = self.core, self.core.lib
         self.enqueue_schedule()
         for s, Bs in enumerate(self.train_sizes):
@@ -353,61 +369,109 @@ class EpochRunner:
                 p.idx = keep
             _lib.check(lib.eav_epoch_accumulate(_ptr(p.loss), None, c.M, _ptr(self.train_acc), _stream()),
                        "eav_epoch_accumulate")
+
+    def _enqueue_val(self, snapshot):
+        """The validation pass (EEGNet_tor.py:118-135) on the live parameters, or on the snapshot with its own workspace."""
+        c, lib = self.core, self.core.lib
         for v, Bv in enumerate(self.val_sizes):
-            p = c.program(Bv, False, "eval")
+            p = c.program(Bv, False, "eval_snap" if snapshot else "eval")
             keep = p.idx
             p.idx = self.val_idx[v]
+            if snapshot:
+                p.params, p.bn_state, p.workspace = self.params_val, self.bn_val, self.ws_val
             try:
                 p.enqueue()
             finally:
                 p.idx = keep
             _lib.check(lib.eav_epoch_accumulate(_ptr(p.loss), _ptr(p.ncorrect), c.M, _ptr(self.val_acc), _stream()),
                        "eav_epoch_accumulate")
-        _lib.check(lib.eav_epoch_commit(_ptr(self.train_acc), _ptr(self.val_acc), c.M, len(self.train_sizes),
-                                        len(self.val_sizes), self.n_test, _ptr(self.history), self.max_epochs,
-                                        _ptr(self.epoch_dev), _stream()), "eav_epoch_commit")
+
+    def _commit(self, with_val_of_this_epoch):
+        c, lib = self.core, self.core.lib
+        _lib.check(lib.eav_epoch_commit(_ptr(self.train_acc), _ptr(self.val_acc) if with_val_of_this_epoch else None, c.M,
+                                        len(self.train_sizes), len(self.val_sizes), self.n_test, _ptr(self.history),
+                                        self.max_epochs, _ptr(self.epoch_dev), _stream()), "eav_epoch_commit")
+
+    def _commit_val_of_previous_epoch(self):
+        c, lib = self.core, self.core.lib
+        _lib.check(lib.eav_epoch_commit_val(_ptr(self.val_acc), c.M, len(self.val_sizes), self.n_test, _ptr(self.history),
+                                            self.max_epochs, _ptr(self.epoch_dev), -1, _stream()), "eav_epoch_commit_val")
+
+    def _enqueue(self, bn_train, with_val=False):
+        c = self.core
+        if not self.pipeline:
+            self._enqueue_train(bn_train)
+            self._enqueue_val(False)
+            self._commit(True)
+            return
+        cur = torch.cuda.current_stream()
+        if with_val:                                    # previous epoch's validation: a parallel branch on the snapshot
+            self._val_stream.wait_stream(cur)
+            with torch.cuda.stream(self._val_stream):
+                self._enqueue_val(True)
+        self._enqueue_train(bn_train)
+        if with_val:
+            cur.wait_stream(self._val_stream)
+            self._commit_val_of_previous_epoch()
+        self.params_val.copy_(c.params)                 # what validate() sees at the end of this epoch
+        self.bn_val.copy_(c.bn_state)
+        self._commit(False)
 
     def _state(self):
         c = self.core
-        return (c.params, c.grads, c.exp_avg, c.exp_avg_sq, c.bn_state, c.step_dev, self.epoch_dev, self.train_acc,
-                self.val_acc, self.history)
+        st = (c.params, c.grads, c.exp_avg, c.exp_avg_sq, c.bn_state, c.step_dev, self.epoch_dev, self.train_acc,
+              self.val_acc, self.history)
+        return st + ((self.params_val, self.bn_val) if self.pipeline else ())
 
-    def capture(self, bn_train):
+    def capture(self, bn_train, with_val=False):
         """Warm-up (really runs one epoch on a side stream), capture, roll every piece of state back."""
         with _on(self.core.device):
-            return self._capture(bn_train)
+            return self._capture(bn_train, with_val)
 
-    def _capture(self, bn_train):
+    def _capture(self, bn_train, with_val):
         snap = [t.clone() for t in self._state()]
         s = torch.cuda.Stream(device=self.core.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self.enqueue(bn_train)
+            self.enqueue(bn_train, with_val)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.enqueue(bn_train)
+            self.enqueue(bn_train, with_val)
         for t, v in zip(self._state(), snap):
             t.copy_(v)
         torch.cuda.synchronize()
-        self._graphs[bool(bn_train)] = g
+        self._graphs[(bool(bn_train), bool(with_val))] = g
         return g
 
     def run_epoch(self, bn_train, use_graph=True):
         """Advance every model by one epoch (asynchronous: returns after the launch)."""
+        with_val = self.pipeline and self._val_pending
         if not use_graph:
-            return self.enqueue(bn_train)
-        g = self._graphs.get(bool(bn_train))
-        if g is None:
-            g = self.capture(bn_train)
-        g.replay()
+            self.enqueue(bn_train, with_val)
+        else:
+            g = self._graphs.get((bool(bn_train), bool(with_val)))
+            if g is None:
+                g = self.capture(bn_train, with_val)
+            g.replay()
+        self._val_pending = self.pipeline
+
+    def finish(self):
+        """Pipelined mode: the validation pass of the last trained epoch (no-op otherwise / when none is pending)."""
+        if not (self.pipeline and self._val_pending):
+            return
+        with _on(self.core.device):
+            self._enqueue_val(True)
+            self._commit_val_of_previous_epoch()
+        self._val_pending = False
 
     def epochs_done(self):
         return int(self.epoch_dev.item())
 
     def results(self):
         """(history [epochs_done][M][3] CPU float32) -- one synchronisation."""
+        self.finish()
         n = self.epochs_done()
         return self.history[:min(n, self.max_epochs)].cpu()
 

@@ -271,6 +271,12 @@ int eav_epoch_accumulate(const float *loss, const int32_t *n_correct, int32_t n_
 int eav_epoch_commit(double *train_acc, double *val_acc, int32_t n_models, int32_t n_train_steps,
                      int32_t n_val_steps, int32_t n_val, float *history, int32_t max_epochs,
                      int64_t *epoch_dev, void *stream);
+/* When the validation pass of epoch e is pipelined with the training of epoch e+1 (it runs on a snapshot of the
+ * parameters taken at the end of epoch e), eav_epoch_commit is called with val_acc == NULL and the validation columns
+ * of history[(*epoch_dev + epoch_offset) % max_epochs] are filled one graph later by this call (epoch_offset = -1
+ * after the next epoch's commit).  Zeroes val_acc; does not touch the epoch counter. */
+int eav_epoch_commit_val(double *val_acc, int32_t n_models, int32_t n_val_steps, int32_t n_val, float *history,
+                         int32_t max_epochs, const int64_t *epoch_dev, int32_t epoch_offset, void *stream);
 
 /* ------------------------------------------------------------------------- */
 /* ShallowConvNet of Transformer_torch/Transformer_EEG.py:107-148: Conv2d(1,40,(1,13)) -> 40

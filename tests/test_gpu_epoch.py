@@ -52,12 +52,13 @@ def test_schedule_is_a_permutation_keyed_by_subject():
     assert torch.equal(torch.cat([t.reshape(-1) for t in solo]), mine)
 
 
+@pytest.mark.parametrize("pipeline", [True, False])
 @pytest.mark.parametrize("M", [1, 3])
-def test_epoch_graph_equals_step_by_step(M):
+def test_epoch_graph_equals_step_by_step(M, pipeline):
     n_tr, n_te, B = 88, 40, 32                 # 3 train steps (32, 32, 24) + 2 validation batches (32, 8)
     x, y = _data(M, n_tr, n_te, seed=3)
     a, b = _core(M, x, y, B), _core(M, x, y, B)
-    ra = a.epoch_runner(n_tr, n_te, B, seed=123, max_epochs=8)
+    ra = a.epoch_runner(n_tr, n_te, B, seed=123, max_epochs=8, pipeline_validation=pipeline)   # validation of epoch e inside graph e+1, or in between
     rb = b.epoch_runner(n_tr, n_te, B, seed=123, max_epochs=8)
     n_epochs = 3
     for e in range(n_epochs):                  # A: one graph replay per epoch
