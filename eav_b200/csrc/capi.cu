@@ -260,20 +260,21 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
     }
     switch (stage) {
         case ST_TCONV_FWD: return launch_tconv_fwd(d, a.x, a.x_index, a.params, WS(float, w.tcw), WS(float, w.y1), pstat, nullptr, st);
-        case ST_BN1: return launch_bn_finalize(d, 1, part, rows1, W * d.B * d.C * d.T, dp_bn ? sums(1, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf1), st);
+        case ST_BN1:
+            if (!d.bn_train)     // eval mode: all three layers at once (ST_BN2 / ST_BN3 are then no-ops)
+                return launch_bn_eval_finalize_all(d, a.params, a.bn_state, WS(float4, w.bnf1), WS(float4, w.bnf2), WS(float4, w.bnf3), st);
+            return launch_bn_finalize(d, 1, part, rows1, W * d.B * d.C * d.T, dp_bn ? sums(1, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf1), st);
         case ST_DW_FWD:
-            if (dw_fwd_fuses_pool(d)) {   // eval mode: BN2's affine is known up front -> finalize first, pool inside dw_fwd
-                TRY(launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st));
+            if (dw_fwd_fuses_pool(d)) {   // eval mode: BN2's affine is known up front (ST_BN1 wrote it), pool inside dw_fwd
                 return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr,
                                      WS(float4, w.bnf2), WS(float, w.d1), st);
             }
             return launch_dw_fwd(d, WS(float, w.y1), a.params, WS(float4, w.bnf1), WS(float, w.y2), pstat, nullptr, nullptr, nullptr, st);
-        case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34)
-            if (tor && d.norm_rate > 0.f)
-                return launch_renorm_rows(a.params + d.oW2, (int64_t)d.M * d.G, d.C, d.C, d.G, d.pstride, d.norm_rate, st);
+        case ST_RENORM_W2:   // hook after the layer used W_old (EEGNet_tor.py:33-34): nothing reads W2 again before the
+                             // backward pass, so both hooks run as ONE launch at ST_RENORM_WD
             return 0;
         case ST_BN2:
-            if (dw_fwd_fuses_pool(d)) return 0;
+            if (!d.bn_train) return 0;
             return launch_bn_finalize(d, 2, part, rows2, W * d.B * d.T, dp_bn ? sums(2, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf2), st);
         case ST_POOL1_FWD:
             if (dw_fwd_fuses_pool(d)) return 0;
@@ -282,12 +283,14 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
             if (tor) return launch_sepconv_fwd(d, WS(float, w.d1), a.params, WS(float, w.tcw2), WS(float, w.y3), pstat, nullptr, st);
             TRY(launch_dwt_fwd(d, WS(float, w.d1), a.params, WS(float, w.y3d), st));
             return launch_pw_fwd(d, WS(float, w.y3d), a.params, WS(float, w.y3), pstat, nullptr, st);
-        case ST_BN3: return launch_bn_finalize(d, 3, part, rows3, W * d.B * d.T4, dp_bn ? sums(3, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf3), st);
+        case ST_BN3:
+            if (!d.bn_train) return 0;
+            return launch_bn_finalize(d, 3, part, rows3, W * d.B * d.T4, dp_bn ? sums(3, false) : nullptr, a.params, a.bn_state, WS(float4, w.bnf3), st);
         case ST_TAIL_FWD:
             return launch_tail_fwd(d, WS(float, w.y3), WS(float4, w.bnf3), a.mask2, a.params, WS(float, w.feat), a.out, WS(float, w.probs), st);
-        case ST_RENORM_WD:   // hook on dense (EEGNet_tor.py:47-48)
+        case ST_RENORM_WD:   // hooks on depthwiseConv and dense (EEGNet_tor.py:33-34,47-48)
             if (tor && d.norm_rate > 0.f)
-                return launch_renorm_rows(a.params + d.oWd, (int64_t)d.M * d.NC, d.FEAT, d.FEAT, d.NC, d.pstride, d.norm_rate, st);
+                return launch_renorm_two(a.params + d.oW2, d.G, d.C, a.params + d.oWd, d.NC, d.FEAT, d.M, d.pstride, d.norm_rate, st);
             return 0;
         case ST_TAIL_BWD:
             return launch_tail_bwd(d, a.dout, WS(float, w.probs), a.params, WS(float, w.y3), WS(float4, w.bnf3), a.mask2,
@@ -326,9 +329,8 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
                 const int S = tconv_bwd_dw_tc_splits(d);
                 TRY(launch_tconv_bwd_fused_tc(d, a.x, a.x_index, WS(float, w.dz2), WS(float, w.y1), WS(float4, w.bnf1),
                                               WS(float4, w.bnf2), a.params, partw, partw2, part, a.grads, S, st));
-                TRY(launch_reduce_partials(partw, S, (int64_t)d.F1 * d.K1, d.M, d.pstride, a.grads + d.oW1, st));
-                return launch_bn_bwd_finalize(d, 1, part, S, W * d.B * d.C * d.T, nullptr, a.params, WS(float4, w.bnf1),
-                                              WS(float4, w.bnb1), a.grads, st);
+                return launch_block1_bwd_finalize(d, partw2, partw, part, S, a.params, WS(float4, w.bnf1), WS(float4, w.bnf2),
+                                                  WS(float4, w.bnb1), a.grads, st);
             }
             return launch_tconv_bwd_dw(d, a.x, a.x_index, WS(float, w.dz1), WS(float, w.y1), WS(float4, w.bnf1), WS(float4, w.bnb1),
                                        partw, a.grads, st);

@@ -316,6 +316,37 @@ __global__ void bn_finalize_kernel(const float *__restrict__ part, int rows_per_
     }
 }
 
+// Eval mode: the three BatchNorm layers are per-channel affines of the running statistics, known before any
+// activation exists -> ONE launch at the start of the forward instead of three small ones.
+__global__ void bn_eval_finalize_all_kernel(const float *__restrict__ params, int64_t pstride, const float *__restrict__ bn_state,
+                                            int64_t bnstride, int F1, int G, int F2, int64_t og1, int64_t ob1, int64_t og2,
+                                            int64_t ob2, int64_t og3, int64_t ob3, int64_t orm1, int64_t orv1, int64_t orm2,
+                                            int64_t orv2, int64_t orm3, int64_t orv3, float eps, float4 *__restrict__ s1,
+                                            float4 *__restrict__ s2, float4 *__restrict__ s3) {
+    const int m = blockIdx.x;
+    for (int i = threadIdx.x; i < F1 + G + F2; i += blockDim.x) {
+        int c, ch;
+        int64_t og, ob, orm, orv;
+        float4 *dst;
+        if (i < F1) { c = i; ch = F1; og = og1; ob = ob1; orm = orm1; orv = orv1; dst = s1; }
+        else if (i < F1 + G) { c = i - F1; ch = G; og = og2; ob = ob2; orm = orm2; orv = orv2; dst = s2; }
+        else { c = i - F1 - G; ch = F2; og = og3; ob = ob3; orm = orm3; orv = orv3; dst = s3; }
+        const float mean = bn_state[(int64_t)m * bnstride + orm + c], var = bn_state[(int64_t)m * bnstride + orv + c];
+        const float invstd = 1.0f / sqrtf(var + eps);
+        const float scale = params[(int64_t)m * pstride + og + c] * invstd;
+        dst[(int64_t)m * ch + c] = make_float4(mean, invstd, scale, params[(int64_t)m * pstride + ob + c] - mean * scale);
+    }
+}
+
+int launch_bn_eval_finalize_all(const NetDims &d, const float *params, const float *bn_state, float4 *s1, float4 *s2,
+                                float4 *s3, cudaStream_t st) {
+    bn_eval_finalize_all_kernel<<<d.M, 160, 0, st>>>(params, d.pstride, bn_state, d.bnstride, d.F1, d.G, d.F2, d.og1, d.ob1,
+                                                     d.og2, d.ob2, d.og3, d.ob3, d.orm1, d.orv1, d.orm2, d.orv2, d.orm3,
+                                                     d.orv3, d.eps, s1, s2, s3);
+    EAV_CUDA_LAUNCH_CHECK("bn_eval_finalize_all");
+    return 0;
+}
+
 int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
                        double count, const double *sums, const float *params, float *bn_state, float4 *stats,
                        cudaStream_t st) {

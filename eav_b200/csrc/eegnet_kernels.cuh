@@ -31,6 +31,13 @@ int launch_tconv_fwd_tc(const NetDims &d, const float *x, const int32_t *x_index
 int launch_bn_finalize(const NetDims &d, int layer, const float *part, int rows_per_model,
                        double count, const double *sums, const float *params, float *bn_state, float4 *stats,
                        cudaStream_t st);
+// eval mode: all three layers' {mean, invstd, scale, shift} from the running statistics in one launch
+int launch_bn_eval_finalize_all(const NetDims &d, const float *params, const float *bn_state, float4 *s1, float4 *s2,
+                                float4 *s3, cudaStream_t st);
+// block-1 tail of the fused eval-mode backward: dW2 and dW1 partial sums -> grads, BatchNorm-1 gradients, in one launch
+int launch_block1_bwd_finalize(const NetDims &d, const float *partw2, const float *partw1, const float *partbn, int S,
+                               const float *params, const float4 *bnf1, const float4 *bnf2, float4 *bnb1, float *grads,
+                               cudaStream_t st);
 // partial rows -> per-(model, channel) float64 sums (the buffer a data-parallel run all-reduces)
 int launch_bn_reduce(const NetDims &d, int layer, const float *part, int rows_per_model, double *sums,
                      cudaStream_t st);
@@ -101,6 +108,8 @@ int dw_fwd_tiles(const NetDims &d);   // time tiles per (sample, filter) of dw_f
 // ---- small ops -------------------------------------------------------------------
 int launch_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_stride,
                        int64_t rows_per_group, int64_t group_stride, float maxnorm, cudaStream_t st);
+int launch_renorm_two(float *wa, int rows_a, int len_a, float *wb, int rows_b, int len_b, int M, int64_t pstride,
+                      float maxnorm, cudaStream_t st);
 int launch_reduce_partials(const float *part, int n_part, int64_t len, int n_models,
                            int64_t dst_stride, float *dst, cudaStream_t st);
 

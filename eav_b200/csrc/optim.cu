@@ -94,6 +94,37 @@ int launch_renorm_rows(float *w, int64_t n_rows, int64_t row_len, int64_t row_st
     return 0;
 }
 
+// Both max-norm hooks of a model in one launch: rows [0, rows_a) of length len_a at wa, rows [rows_a, rows_a + rows_b)
+// of length len_b at wb (per model).  One warp per row.
+__global__ void renorm_two_kernel(float *__restrict__ wa, int rows_a, int len_a, float *__restrict__ wb, int rows_b, int len_b,
+                                  int M, int64_t pstride, float maxnorm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int per = rows_a + rows_b;
+    if (r >= (int64_t)M * per) return;
+    const int m = (int)(r / per), k = (int)(r - (int64_t)m * per);
+    float *row;
+    int len;
+    if (k < rows_a) { row = wa + (int64_t)m * pstride + (int64_t)k * len_a; len = len_a; }
+    else { row = wb + (int64_t)m * pstride + (int64_t)(k - rows_a) * len_b; len = len_b; }
+    float s = 0.f;
+    for (int i = lane; i < len; i += 32) s = fmaf(row[i], row[i], s);
+    s = warp_sum(s);
+    const float norm = sqrtf(s);
+    if (norm > maxnorm) {
+        const float sc = maxnorm / (norm + 1e-7f);
+        for (int i = lane; i < len; i += 32) row[i] *= sc;
+    }
+}
+
+int launch_renorm_two(float *wa, int rows_a, int len_a, float *wb, int rows_b, int len_b, int M, int64_t pstride,
+                      float maxnorm, cudaStream_t st) {
+    const int64_t rows = (int64_t)M * (rows_a + rows_b);
+    renorm_two_kernel<<<(unsigned)cdiv64(rows, 4), 128, 0, st>>>(wa, rows_a, len_a, wb, rows_b, len_b, M, pstride, maxnorm);
+    EAV_CUDA_LAUNCH_CHECK("renorm_two");
+    return 0;
+}
+
 // =================================================================================
 // nn.CrossEntropyLoss()(out, y): mean_b( logsumexp(out_b) - out_b[y_b] ) and d/d(out).
 // One CTA per model; fixed-order block reduction (deterministic).

@@ -1001,23 +1001,45 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
     if (warp == 12) tc::tmem_dealloc(tmem, 512);
 }
 
-// dW2[m][g][c] = k2[g] * sum over the model's units (in order) and the four time quarters of the per-unit slots.
+// One launch for the tail of the fused backward (three small kernels before: at 5-6 models per GPU a launch costs as much
+// as the work): dW2[m][g][c] = k2[g] * sum over the model's units (in order) and the four time quarters of the per-unit
+// slots; dW1[m][f][k] = sum of the S partial slabs; d(gamma1) / d(beta1) from the S partial BatchNorm sums.
 __global__ void __launch_bounds__(256)
-dw2_fused_reduce_kernel(const float *__restrict__ partw2, int S, int C, const float *__restrict__ params,
-                        int64_t pstride, int64_t og2, int64_t oW2, const float4 *__restrict__ bnf2,
-                        float *__restrict__ grads) {
-    const int m = blockIdx.x, G = 64;
-    for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
-        const int gch = i / C, c = i - gch * C;
-        const int fg = gch >> 5, j = gch & 31;
-        float s = 0.f;
-        for (int sp = 0; sp < S; ++sp) {
-            const float *p = partw2 + (((int64_t)(m * S + sp) * 2 + fg) * 4) * TCX_CMAX * 32 + c * 32 + j;
+block1_bwd_finalize_kernel(const float *__restrict__ partw2, const float *__restrict__ partw1, const float *__restrict__ partbn,
+                           int S, int C, int K1, const float *__restrict__ params, int64_t pstride, int64_t og1, int64_t ob1,
+                           int64_t og2, int64_t oW1, int64_t oW2, const float4 *__restrict__ bnf1,
+                           const float4 *__restrict__ bnf2, float4 *__restrict__ bnb1, float *__restrict__ grads) {
+    const int m = blockIdx.y, G = 64, F1 = 8;
+    const int n2 = G * C, n1 = F1 * K1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2 + n1 + F1; i += gridDim.x * blockDim.x) {
+        if (i < n2) {
+            const int gch = i / C, c = i - gch * C;
+            const int fg = gch >> 5, j = gch & 31;
+            float s = 0.f;
+            for (int sp = 0; sp < S; ++sp) {
+                const float *p = partw2 + (((int64_t)(m * S + sp) * 2 + fg) * 4) * TCX_CMAX * 32 + c * 32 + j;
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) s += p[qq * TCX_CMAX * 32];
+                for (int qq = 0; qq < 4; ++qq) s += p[qq * TCX_CMAX * 32];
+            }
+            const float k2 = params[(int64_t)m * pstride + og2 + gch] * bnf2[(int64_t)m * G + gch].y;
+            grads[(int64_t)m * pstride + oW2 + i] = s * k2;
+        } else if (i < n2 + n1) {
+            const int e = i - n2;
+            const float *p = partw1 + (int64_t)m * S * n1 + e;
+            float s = 0.f;
+            for (int sp = 0; sp < S; ++sp) s += p[(int64_t)sp * n1];
+            grads[(int64_t)m * pstride + oW1 + e] = s;
+        } else {
+            const int f = i - n2 - n1;
+            double s1 = 0.0, s2 = 0.0;
+            for (int sp = 0; sp < S; ++sp) {
+                s1 += (double)partbn[(((int64_t)m * S + sp) * F1 + f) * 2];
+                s2 += (double)partbn[(((int64_t)m * S + sp) * F1 + f) * 2 + 1];
+            }
+            grads[(int64_t)m * pstride + og1 + f] = (float)s2;
+            grads[(int64_t)m * pstride + ob1 + f] = (float)s1;
+            bnb1[(int64_t)m * F1 + f] = make_float4(params[(int64_t)m * pstride + og1 + f] * bnf1[(int64_t)m * F1 + f].y, 0.f, 0.f, 0.f);
         }
-        const float k2 = params[(int64_t)m * pstride + og2 + gch] * bnf2[(int64_t)m * G + gch].y;
-        grads[(int64_t)m * pstride + oW2 + i] = s * k2;
     }
 }
 
@@ -1052,8 +1074,16 @@ int launch_tconv_bwd_fused_tc(const NetDims &d, const float *x, const int32_t *x
                    d.variant == EAV_VARIANT_TOR ? 1 : 0};
     tconv_bwd_fused_tc_kernel<<<grid, TCX_THREADS, smem, st>>>(x, x_index, a, d.M, d.B, d.C, d.T, d.K1, d.pad1l, S);
     EAV_CUDA_LAUNCH_CHECK("tconv_bwd_fused_tc");
-    dw2_fused_reduce_kernel<<<d.M, 256, 0, st>>>(partw2, S, d.C, params, d.pstride, d.og2, d.oW2, bnf2, grads);
-    EAV_CUDA_LAUNCH_CHECK("dw2_fused_reduce");
+    return 0;
+}
+
+int launch_block1_bwd_finalize(const NetDims &d, const float *partw2, const float *partw1, const float *partbn, int S,
+                               const float *params, const float4 *bnf1, const float4 *bnf2, float4 *bnb1, float *grads,
+                               cudaStream_t st) {
+    const int n = 64 * d.C + d.F1 * d.K1 + d.F1;
+    block1_bwd_finalize_kernel<<<dim3(cdiv(n, 256), d.M), 256, 0, st>>>(partw2, partw1, partbn, S, d.C, d.K1, params, d.pstride,
+                                                                        d.og1, d.ob1, d.og2, d.oW1, d.oW2, bnf1, bnf2, bnb1, grads);
+    EAV_CUDA_LAUNCH_CHECK("block1_bwd_finalize");
     return 0;
 }
 
