@@ -816,9 +816,12 @@ def run_subject_workload(args, variant):
         # kernels that is what the step cannot avoid moving once y1 is saved for backward: y1 is written by
         # tconv_fwd, so dw_fwd's compulsory traffic is the y2 write only (+ y1 if it is not fused into the conv
         # epilogue), dw_bwd's is one y1 read + dz2 (+ y2 in train mode); the dz1 round trip is NOT algorithmic.
+        # eval-mode BN: dw_bwd and (for the backward) the dz1 round trip are folded into the tcgen05 dW1 kernel, whose
+        # algorithmic work is then the dW1 correlation (72.0 MFLOP) + the depthwise backward (3.84 MFLOP) per sample
+        fused_bwd = stages.get("dw_bwd", 1.0) < 0.02 and stages.get("tconv_bwd_dw", 0.0) > 0.02
         model = {
             "tconv_fwd": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
-            "tconv_bwd_dw": ("tensor" if tc_on else "fp32", TCONV_FLOP_PER_SAMPLE * N, "flop"),
+            "tconv_bwd_dw": ("tensor" if tc_on else "fp32", (TCONV_FLOP_PER_SAMPLE + (3.84e6 if fused_bwd else 0.0)) * N, "flop"),
             "dw_bwd": ("hbm", 4.0 * N * (8 * 30 * 500 + 64 * 500 * (2 if steady_train else 1)), "byte"),
             "dw_fwd": ("hbm", 4.0 * N * (8 * 30 * 500 + 64 * 500), "byte"),
         }
@@ -830,7 +833,7 @@ def run_subject_workload(args, variant):
         def kernel_roofline(name):
             bound, work, kind = model[name]
             t = stages[name] * 1e-3
-            if t <= 0:
+            if t < 0.02e-3:        # the stage is a no-op in this mode (fused into a neighbour): nothing to rate
                 return None
             if kind == "flop":
                 ach, unit = work / t / 1e12, "TFLOP/s"
@@ -859,6 +862,11 @@ def run_subject_workload(args, variant):
             "hbm": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 7.7 TB/s nominal",
         }[roof["bound"]]
         roof["kernels"] = per_kernel
+        if fused_bwd:
+            roof["fused_backward"] = ("eval-mode BN: the stage `tconv_bwd_dw` is tconv_bwd_fused_tc_kernel = dw_bwd + tconv_bwd_dw of "
+                                      "round 1 in one pass over y1 (dz1 never written); the two separate kernels it replaces took "
+                                      f"{stages_other.get('dw_bwd', 0) + stages_other.get('tconv_bwd_dw', 0):.3f} ms in the other BN mode "
+                                      "of this same run (stage_ms_other_bn_mode)")
         roof["stage_models"] = M
         roof["fp32_ceilings"] = {"ffma_pipe_peak": fp32_peak, "register_outer_product_ffma2": fp32_ffma2,
                                  "note": "CUDA-core ceilings on this device: immediate-operand FFMA loop, and an 8x8 "

@@ -1,19 +1,26 @@
-"""The committed bench line (profiles/r1_bench_tc_n1.json, written by `python bench.py` on a B200) carries every
-key of the driver's contract; guards the JSON shape against regressions without needing a GPU."""
+"""The committed bench lines (profiles/r2_bench_*.json, written by `python bench.py` on B200 boxes) carry every key of
+the driver's contract; guards the JSON shape against regressions without needing a GPU."""
 import json
 import os
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _load(name):
+    return json.load(open(os.path.join(ROOT, "profiles", name)))
+
+
 def test_committed_bench_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_tc_n1.json")))
+    d = _load("r2_bench_n1.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "gpu_launches", "e2e", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
-    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "strong" and d["data"] == "synthetic"
     assert d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "model" not in d["config"]
-    assert abs(d["value"] - 1344 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]      # samples per step / step time
+    c = d["config"]
+    assert c["subjects_total"] == 42 and c["subjects_per_gpu"] == [42] and c["batch_sizes"] == [32] * 8 + [24]
+    # value = training samples of the timed steps / their time
+    assert abs(d["value"] - c["train_samples_in_timed_region"] / (d["ms_per_step"] * d["steps"] * 1e-3)) < 1e-6 * d["value"]
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
     r = d["roofline"]
@@ -21,8 +28,25 @@ def test_committed_bench_line_has_the_contract_keys():
     assert r["unit"] in ("GB/s", "TFLOP/s") and r["traffic"] is not None
     for name, k in r["kernels"].items():
         assert 0 < k["frac"] < 1, name                      # nothing above its roofline
-    c = d["cpu_baseline"]
-    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
     ck = d["clocks"]
     assert ck["sm_mhz"] and ck["sm_max_mhz"] and not set(ck["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown",
                                                                           "sw_thermal_slowdown"}
+    p = d["preprocess"]
+    assert p["roofline"]["bound"] == "hbm" and p["roofline"]["traffic"] and 0 < p["roofline"]["frac"] < 1
+
+
+def test_committed_8gpu_line_is_the_42_subject_workload():
+    d = _load("r2_bench_n8_noreplica.json")
+    assert d["n_gpus"] == 8 and d["scaling"] == "strong"
+    assert d["config"]["subjects_total"] == 42 and d["config"]["subjects_per_gpu"] == [6, 6, 5, 5, 5, 5, 5, 5]
+    assert d["dp_parity"]["ok"] is True
+    one = _load("r2_bench_n1.json")
+    assert 4.5 < d["value"] / one["value"] <= 7.0            # strong scaling of 42 subjects: ceiling 42 / 6 = 7.0
+
+
+def test_reference_arm_line():
+    d = _load("r2_bench_ref.json")
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
