@@ -670,7 +670,10 @@ def run_subject_workload(args, variant):
 
     # ---------------------------------------------------------------- end-to-end: host buffers in, loss out
     # Same K steps (+ the validation batches after each 9th), but every batch starts in pinned HOST memory:
-    # H2D on a copy stream into a double-buffered staging area, per-step graphs through the C ABI, loss D2H per step.
+    # H2D on a copy stream into double-buffered staging areas, per-step graphs through the C ABI, loss D2H per step.
+    # As in the resident path, the validation batches of epoch e run on a snapshot of the parameters on their own
+    # stream while the training steps of epoch e+1 proceed (what validate() would have seen; the max-norm hooks it would
+    # have applied to the live weights are applied explicitly).
     n_ring = 4
     host_x = [torch.empty(M * B, 30, 500, dtype=torch.float32).pin_memory() for _ in range(n_ring)]
     host_y = [torch.empty(M * B, dtype=torch.int64).pin_memory() for _ in range(n_ring)]
@@ -679,11 +682,16 @@ def run_subject_workload(args, variant):
         host_x[r].copy_(x_all.index_select(0, rows).cpu())
         host_y[r].copy_(y_all.index_select(0, rows).cpu())
     host_loss = torch.empty(M, dtype=torch.float32).pin_memory()
+    host_vloss = torch.empty(M, dtype=torch.float32).pin_memory()
     host_corr = torch.empty(M, dtype=torch.int32).pin_memory()
-    stage_x = [torch.empty(M * B, 30, 500, dtype=torch.float32, device=dev) for _ in range(2)]
-    stage_y = [torch.empty(M * B, dtype=torch.int64, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    mk = lambda: ([torch.empty(M * B, 30, 500, dtype=torch.float32, device=dev) for _ in range(2)],
+                  [torch.empty(M * B, dtype=torch.int64, device=dev) for _ in range(2)])
+    (stage_x, stage_y), (vstage_x, vstage_y) = mk(), mk()
+    copy_stream, val_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
+    params_snap, bn_snap = tr.params.clone(), tr.bn_state.clone()
+    ws_val = torch.empty(tr.ws_bytes, dtype=torch.uint8, device=dev)
+    hook_cfg = dims.cfg(M, 1, param_stride=tr.pstride, bn_stride=dims.n_bn)
     items = []                                               # (kind, batch) in the reference's loop order
     for i in range(K):
         items.append(("train", sizes[i % spe]))
@@ -692,39 +700,73 @@ def run_subject_workload(args, variant):
     progs = {}
     for kind, Bs in set(items):
         for slot_i in range(2):
-            progs[(kind, Bs, slot_i)] = tr.host_step_program(Bs, bn_train=steady_train and kind == "train", kind=kind,
-                                                             x_src=stage_x[slot_i], y_src=stage_y[slot_i], slot=slot_i)
+            if kind == "train":
+                p = tr.host_step_program(Bs, bn_train=steady_train, kind="train", x_src=stage_x[slot_i], y_src=stage_y[slot_i],
+                                         slot=slot_i)
+            else:
+                p = tr.host_step_program(Bs, bn_train=False, kind="eval", x_src=vstage_x[slot_i], y_src=vstage_y[slot_i],
+                                         slot=2 + slot_i)
+                p.params, p.bn_state, p.workspace = params_snap, bn_snap, ws_val
+            progs[(kind, Bs, slot_i)] = p
     h2d_total = [0]
 
     def e2e_steps(items):
-        ev_copied = [torch.cuda.Event() for _ in range(2)]
-        ev_used = [torch.cuda.Event() for _ in range(2)]
         h2d_total[0] = 0
+        ev_copied = {k: [torch.cuda.Event() for _ in range(2)] for k in ("train", "eval")}
+        ev_used = {k: [torch.cuda.Event() for _ in range(2)] for k in ("train", "eval")}
+        count = {"train": 0, "eval": 0}
+        seq = {"train": [i for i, it in enumerate(items) if it[0] == "train"],
+               "eval": [i for i, it in enumerate(items) if it[0] == "eval"]}
+        issued = {"train": 0, "eval": 0}                     # H2D copies issued so far, per kind
 
-        def copy_in(i, slot_i):
+        def issue_copy(kind):
+            """H2D of the next not-yet-copied item of `kind` into its staging slot (one item ahead of its consumer)."""
+            j = issued[kind]
+            if j >= len(seq[kind]):
+                return
+            i, slot_i = seq[kind][j], j & 1
             n = M * items[i][1]
-            stage_x[slot_i][:n].copy_(host_x[i % n_ring][:n], non_blocking=True)
-            stage_y[slot_i][:n].copy_(host_y[i % n_ring][:n], non_blocking=True)
+            sx, sy = (stage_x, stage_y) if kind == "train" else (vstage_x, vstage_y)
+            with torch.cuda.stream(copy_stream):
+                if j >= 2:
+                    copy_stream.wait_event(ev_used[kind][slot_i])
+                sx[slot_i][:n].copy_(host_x[i % n_ring][:n], non_blocking=True)
+                sy[slot_i][:n].copy_(host_y[i % n_ring][:n], non_blocking=True)
+                ev_copied[kind][slot_i].record(copy_stream)
             h2d_total[0] += n * (30 * 500 * 4 + 8)
+            issued[kind] += 1
 
-        with torch.cuda.stream(copy_stream):
-            copy_in(0, 0)
-            ev_copied[0].record(copy_stream)
-        for i, (kind, Bs) in enumerate(items):
-            cur, nxt = i & 1, (i + 1) & 1
-            if i + 1 < len(items):                          # H2D of item i+1 overlaps the kernels of item i
-                with torch.cuda.stream(copy_stream):
-                    if i >= 1:
-                        copy_stream.wait_event(ev_used[nxt])
-                    copy_in(i + 1, nxt)
-                    ev_copied[nxt].record(copy_stream)
-            main_stream.wait_event(ev_copied[cur])
-            p = progs[(kind, Bs, cur)]
-            p.run()
-            ev_used[cur].record(main_stream)
-            host_loss.copy_(p.loss, non_blocking=True)      # D2H of the step's result
-            if kind == "eval":
-                host_corr.copy_(p.ncorrect, non_blocking=True)
+        issue_copy("train")
+        issue_copy("eval")
+        prev_kind = None
+        for kind, Bs in items:
+            j = count[kind]
+            slot_i = j & 1
+            issue_copy(kind)                                 # the copy of this kind's NEXT item overlaps this item's kernels
+            if kind == "train":
+                main_stream.wait_event(ev_copied[kind][slot_i])
+                p = progs[(kind, Bs, slot_i)]
+                p.run()
+                ev_used[kind][slot_i].record(main_stream)
+                host_loss.copy_(p.loss, non_blocking=True)   # D2H of the step's result
+            else:
+                if prev_kind == "train":                     # epoch end: snapshot for this epoch's validation pass
+                    main_stream.wait_stream(val_stream)      # (the previous pass has finished reading the old snapshot)
+                    params_snap.copy_(tr.params, non_blocking=True)
+                    bn_snap.copy_(tr.bn_state, non_blocking=True)
+                    _lib.check(lib.eav_eegnet_apply_hooks(ctypes.byref(hook_cfg), ops._ptr(tr.params), ops._stream()),
+                               "eav_eegnet_apply_hooks")
+                    val_stream.wait_stream(main_stream)
+                with torch.cuda.stream(val_stream):
+                    val_stream.wait_event(ev_copied[kind][slot_i])
+                    p = progs[(kind, Bs, slot_i)]
+                    p.run()
+                    ev_used[kind][slot_i].record(val_stream)
+                    host_vloss.copy_(p.loss, non_blocking=True)
+                    host_corr.copy_(p.ncorrect, non_blocking=True)
+            count[kind] += 1
+            prev_kind = kind
+        main_stream.wait_stream(val_stream)
         torch.cuda.synchronize()
 
     e2e_steps(items[:min(len(items), 2 * spe + 8)])          # warm-up: captures the per-(batch, kind, slot) graphs
@@ -929,9 +971,10 @@ def run_subject_workload(args, variant):
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_total_ms / K,
                     "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
                     "how": "the same K steps (+ validation batches) with every batch in pinned host memory: "
-                           "cudaMemcpyAsync on a copy stream into a double-buffered staging area -> "
-                           "eav_eegnet_forward/loss/backward/adam through the C ABI (per-step CUDA graphs) -> loss "
-                           "(and #correct) D2H every step; bytes are summed over all ranks"},
+                           "cudaMemcpyAsync on a copy stream into double-buffered staging areas -> "
+                           "eav_eegnet_forward/loss/backward/adam through the C ABI (per-step CUDA graphs; the validation "
+                           "batches of an epoch run on a parameter snapshot on a second stream, overlapping the next "
+                           "epoch's steps) -> loss (and #correct) D2H every step; bytes are summed over all ranks"},
             "clocks": clk}
     if replica is not None:
         line["replica_throughput"] = replica

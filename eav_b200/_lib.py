@@ -52,6 +52,7 @@ SYMBOLS = {
     "eav_eegnet_workspace_offsets": (c_int, [POINTER(EegnetCfg), POINTER(c_size_t)]),
     "eav_eegnet_forward": (c_int, [POINTER(EegnetCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "eav_eegnet_apply_hooks": (c_int, [POINTER(EegnetCfg), c_void_p, c_void_p]),
     "eav_eegnet_loss": (c_int, [POINTER(EegnetCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
     "eav_eegnet_backward": (c_int, [POINTER(EegnetCfg), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

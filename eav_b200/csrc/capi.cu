@@ -445,3 +445,15 @@ extern "C" int eav_eegnet_backward(const eav_eegnet_cfg *cfg, const float *x, co
     }
     return 0;
 }
+
+// The two max-norm forward hooks (EEGNet_tor.py:33-34,47-48) on their own: what a forward pass leaves behind in the
+// weights.  Used when the validation forward runs on a SNAPSHOT of the parameters (pipelined validation): the reference's
+// validate() forward would have renormed the live weights, so the live copy gets the same treatment.
+extern "C" int eav_eegnet_apply_hooks(const eav_eegnet_cfg *cfg, float *params, void *stream) {
+    NetDims d;
+    TRY(make_dims(cfg, &d));
+    EAV_REQUIRE(params != nullptr, EAV_ERR_BAD_ARG, "eegnet_apply_hooks: null pointer");
+    if (d.variant != EAV_VARIANT_TOR || d.norm_rate <= 0.f) return 0;
+    return launch_renorm_two(params + d.oW2, d.G, d.C, params + d.oWd, d.NC, d.FEAT, d.M, d.pstride, d.norm_rate,
+                             (cudaStream_t)stream);
+}

@@ -415,6 +415,10 @@ class EpochRunner:
             self._commit_val_of_previous_epoch()
         self.params_val.copy_(c.params)                 # what validate() sees at the end of this epoch
         self.bn_val.copy_(c.bn_state)
+        # validate()'s forward also leaves its max-norm hooks' renorm in the LIVE weights (EEGNet_tor.py:33-34,47-48);
+        # the pipelined pass will only renorm the snapshot
+        cfg = c.dims.cfg(c.M, 1, param_stride=c.pstride, bn_stride=c.dims.n_bn)
+        _lib.check(c.lib.eav_eegnet_apply_hooks(ctypes.byref(cfg), _ptr(c.params), _stream()), "eav_eegnet_apply_hooks")
         self._commit(False)
 
     def _state(self):

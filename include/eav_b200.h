@@ -171,6 +171,11 @@ int eav_eegnet_forward(const eav_eegnet_cfg *cfg, const float *x, const int32_t 
                        const uint8_t *mask2, float *out, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* The side effect a forward pass has on the weights -- the two max-norm hooks of variant 0 (EEGNet_tor.py:33-34,47-48:
+ * rows of depthwiseConv.weight and dense.weight renormed to L2 <= norm_rate) -- without the forward pass.  No-op for
+ * variant 1 or norm_rate <= 0. */
+int eav_eegnet_apply_hooks(const eav_eegnet_cfg *cfg, float *params, void *stream);
+
 /*
  * nn.CrossEntropyLoss()(out, targets) per model (EEGNet_tor.py:81,105) and its
  * gradient w.r.t. `out`.
