@@ -762,7 +762,8 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                 const float4 st = a.bnf1[(int64_t)m * F1 + fg * 4 + fp * 2 + h];
                 sc1[h] = st.z; sh1[h] = st.w; is1[h] = st.y; nmi[h] = -st.x * st.y;
             }
-            float p1[2] = {0.f, 0.f}, p2[2] = {0.f, 0.f};
+            // BatchNorm-1 backward sums as packed pairs (even / odd time steps), folded at the end of the unit
+            float2 p1p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, p2p[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
             int b = r_lo / C, c = r_lo - b * C;
             // The cross-lane sum of a row's 16 dW2 accumulators is a chain of 5 dependent shuffles; it is issued one
             // row late, in the same basic block as the next row's FFMA work, so its latency hides under that work.
@@ -804,37 +805,46 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                     const float4 v0 = *reinterpret_cast<const float4 *>(vtab + c * 32 + fp * 16 + h * 8);
                     const float4 v1 = *reinterpret_cast<const float4 *>(vtab + c * 32 + fp * 16 + h * 8 + 4);
                     const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    const float yy[4] = {yv[h].x, yv[h].y, yv[h].z, yv[h].w};
-                    float oo[4];
-#pragma unroll
-                    for (int dd = 0; dd < 8; ++dd) acc[h * 8 + dd] = 0.f;
+                    // Packed fp32 (Blackwell FFMA2 / FMUL2 / FADD2 on 64-bit register pairs): the four time steps of the
+                    // thread are two (even, odd) pairs, which is how dz2 already sits in its float4 registers -- the 16 FMAs
+                    // per element of the two small contractions become 8 instructions.
+                    const float2 y01 = make_float2(yv[h].x, yv[h].y), y23 = make_float2(yv[h].z, yv[h].w);
+                    const float2 sc2 = make_float2(sc1[h], sc1[h]), sh2 = make_float2(sh1[h], sh1[h]);
+                    const float2 pre01 = __ffma2_rn(y01, sc2, sh2), pre23 = __ffma2_rn(y23, sc2, sh2);
+                    const float pre[4] = {pre01.x, pre01.y, pre23.x, pre23.y};
+                    float ep[4], act[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float pre = fmaf(yy[e], sc1[h], sh1[h]);
-                        float ep = 1.f, act = pre;
+                        ep[e] = 1.f;
+                        act[e] = pre[e];
                         if (a.elu1) {
                             // exp(pre) as ONE multiply + MUFU.EX2: the .ftz form needs no denormal pre-scale / post-square
                             // (4 more instructions per element with __expf); results below 2^-126 flush to 0, harmless
                             // for exp(x) - 1 and for a derivative that multiplies a gradient.
                             float ex;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre * 1.4426950408889634f));
-                            const bool pos = pre > 0.f;
-                            ep = pos ? 1.f : ex;
-                            act = pos ? pre : ex - 1.f;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(pre[e] * 1.4426950408889634f));
+                            const bool pos = pre[e] > 0.f;
+                            ep[e] = pos ? 1.f : ex;
+                            act[e] = pos ? pre[e] : ex - 1.f;
                         }
-                        float uu = 0.f;
-#pragma unroll
-                        for (int dd = 0; dd < 8; ++dd) {
-                            const float dzv = e == 0 ? dzr[h][dd].x : e == 1 ? dzr[h][dd].y : e == 2 ? dzr[h][dd].z : dzr[h][dd].w;
-                            uu = fmaf(vv[dd], dzv, uu);
-                            acc[h * 8 + dd] = fmaf(dzv, act, acc[h * 8 + dd]);
-                        }
-                        const float dz = uu * ep;
-                        p1[h] += dz;
-                        p2[h] = fmaf(dz, fmaf(yy[e], is1[h], nmi[h]), p2[h]);
-                        oo[e] = dz;
                     }
-                    outv[h] = make_float4(oo[0], oo[1], oo[2], oo[3]);
+                    const float2 act01 = make_float2(act[0], act[1]), act23 = make_float2(act[2], act[3]);
+                    float2 uu01 = make_float2(0.f, 0.f), uu23 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int dd = 0; dd < 8; ++dd) {
+                        const float2 d01 = make_float2(dzr[h][dd].x, dzr[h][dd].y), d23 = make_float2(dzr[h][dd].z, dzr[h][dd].w);
+                        const float2 w2 = make_float2(vv[dd], vv[dd]);
+                        uu01 = __ffma2_rn(w2, d01, uu01);
+                        uu23 = __ffma2_rn(w2, d23, uu23);
+                        const float2 a2 = __ffma2_rn(d23, act23, __fmul2_rn(d01, act01));
+                        acc[h * 8 + dd] = a2.x + a2.y;
+                    }
+                    const float2 dz01 = __fmul2_rn(uu01, make_float2(ep[0], ep[1])), dz23 = __fmul2_rn(uu23, make_float2(ep[2], ep[3]));
+                    const float2 is2 = make_float2(is1[h], is1[h]), nm2 = make_float2(nmi[h], nmi[h]);
+                    p1p[h] = __fadd2_rn(__fadd2_rn(p1p[h], dz01), dz23);
+                    p2p[h] = __ffma2_rn(dz01, __ffma2_rn(y01, is2, nm2), p2p[h]);
+                    p2p[h] = __ffma2_rn(dz23, __ffma2_rn(y23, is2, nm2), p2p[h]);
+                    outv[h] = make_float4(dz01.x, dz01.y, dz23.x, dz23.y);
                 }
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bar_in_empty[ib]);          // the loader may refill this input buffer
@@ -872,7 +882,9 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
             if (cprev >= 0) flush_dw2();
             // ---- end of unit: dW2 slots and BatchNorm-1 sums -> global partials (fixed order)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) { p1[h] = warp_sum(p1[h]); p2[h] = warp_sum(p2[h]); }
+            float p1[2], p2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { p1[h] = warp_sum(p1p[h].x + p1p[h].y); p2[h] = warp_sum(p2p[h].x + p2p[h].y); }
             if (lane == 0) { bnred[pw * 4 + 0] = p1[0]; bnred[pw * 4 + 1] = p2[0]; bnred[pw * 4 + 2] = p1[1]; bnred[pw * 4 + 3] = p2[1]; }
             producers_sync();
             const int sp = (u >> 1) - m * S;
