@@ -670,7 +670,8 @@ def run_subject_workload(args, variant):
 
     # ---------------------------------------------------------------- end-to-end: host buffers in, loss out
     # Same K steps (+ the validation batches after each 9th), but every batch starts in pinned HOST memory:
-    # H2D on a copy stream into double-buffered staging areas, per-step graphs through the C ABI, loss D2H per step.
+    # H2D into a 3-deep ring of staging buffers (one copy stream for the training batches, one for the validation batches,
+    # so that neither queue waits behind the other's buffer hand-back), per-step graphs through the C ABI, loss D2H per step.
     # As in the resident path, the validation batches of epoch e run on a snapshot of the parameters on their own
     # stream while the training steps of epoch e+1 proceed (what validate() would have seen; the max-norm hooks it would
     # have applied to the live weights are applied explicitly).
@@ -684,10 +685,12 @@ def run_subject_workload(args, variant):
     host_loss = torch.empty(M, dtype=torch.float32).pin_memory()
     host_vloss = torch.empty(M, dtype=torch.float32).pin_memory()
     host_corr = torch.empty(M, dtype=torch.int32).pin_memory()
-    mk = lambda: ([torch.empty(M * B, 30, 500, dtype=torch.float32, device=dev) for _ in range(2)],
-                  [torch.empty(M * B, dtype=torch.int64, device=dev) for _ in range(2)])
+    R = 3                                                    # staging ring depth: copies run R - 1 items ahead
+    mk = lambda: ([torch.empty(M * B, 30, 500, dtype=torch.float32, device=dev) for _ in range(R)],
+                  [torch.empty(M * B, dtype=torch.int64, device=dev) for _ in range(R)])
     (stage_x, stage_y), (vstage_x, vstage_y) = mk(), mk()
-    copy_stream, val_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    copy_streams = {"train": torch.cuda.Stream(device=dev), "eval": torch.cuda.Stream(device=dev)}
+    val_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
     params_snap, bn_snap = tr.params.clone(), tr.bn_state.clone()
     ws_val = torch.empty(tr.ws_bytes, dtype=torch.uint8, device=dev)
@@ -699,36 +702,37 @@ def run_subject_workload(args, variant):
             items += [("eval", Bv) for Bv in runner.val_sizes]
     progs = {}
     for kind, Bs in set(items):
-        for slot_i in range(2):
+        for slot_i in range(R):
             if kind == "train":
                 p = tr.host_step_program(Bs, bn_train=steady_train, kind="train", x_src=stage_x[slot_i], y_src=stage_y[slot_i],
                                          slot=slot_i)
             else:
                 p = tr.host_step_program(Bs, bn_train=False, kind="eval", x_src=vstage_x[slot_i], y_src=vstage_y[slot_i],
-                                         slot=2 + slot_i)
+                                         slot=R + slot_i)
                 p.params, p.bn_state, p.workspace = params_snap, bn_snap, ws_val
             progs[(kind, Bs, slot_i)] = p
     h2d_total = [0]
 
     def e2e_steps(items):
         h2d_total[0] = 0
-        ev_copied = {k: [torch.cuda.Event() for _ in range(2)] for k in ("train", "eval")}
-        ev_used = {k: [torch.cuda.Event() for _ in range(2)] for k in ("train", "eval")}
+        ev_copied = {k: [torch.cuda.Event() for _ in range(R)] for k in ("train", "eval")}
+        ev_used = {k: [torch.cuda.Event() for _ in range(R)] for k in ("train", "eval")}
         count = {"train": 0, "eval": 0}
         seq = {"train": [i for i, it in enumerate(items) if it[0] == "train"],
                "eval": [i for i, it in enumerate(items) if it[0] == "eval"]}
         issued = {"train": 0, "eval": 0}                     # H2D copies issued so far, per kind
 
         def issue_copy(kind):
-            """H2D of the next not-yet-copied item of `kind` into its staging slot (one item ahead of its consumer)."""
+            """H2D of the next not-yet-copied item of `kind` into its staging slot (R - 1 items ahead of its consumer)."""
             j = issued[kind]
             if j >= len(seq[kind]):
                 return
-            i, slot_i = seq[kind][j], j & 1
+            i, slot_i = seq[kind][j], j % R
             n = M * items[i][1]
             sx, sy = (stage_x, stage_y) if kind == "train" else (vstage_x, vstage_y)
+            copy_stream = copy_streams[kind]
             with torch.cuda.stream(copy_stream):
-                if j >= 2:
+                if j >= R:
                     copy_stream.wait_event(ev_used[kind][slot_i])
                 sx[slot_i][:n].copy_(host_x[i % n_ring][:n], non_blocking=True)
                 sy[slot_i][:n].copy_(host_y[i % n_ring][:n], non_blocking=True)
@@ -736,13 +740,14 @@ def run_subject_workload(args, variant):
             h2d_total[0] += n * (30 * 500 * 4 + 8)
             issued[kind] += 1
 
-        issue_copy("train")
-        issue_copy("eval")
+        for _ in range(R - 1):
+            issue_copy("train")
+            issue_copy("eval")
         prev_kind = None
         for kind, Bs in items:
             j = count[kind]
-            slot_i = j & 1
-            issue_copy(kind)                                 # the copy of this kind's NEXT item overlaps this item's kernels
+            slot_i = j % R
+            issue_copy(kind)                                 # copies of this kind's NEXT items overlap this item's kernels
             if kind == "train":
                 main_stream.wait_event(ev_copied[kind][slot_i])
                 p = progs[(kind, Bs, slot_i)]
@@ -769,7 +774,8 @@ def run_subject_workload(args, variant):
         main_stream.wait_stream(val_stream)
         torch.cuda.synchronize()
 
-    e2e_steps(items[:min(len(items), 2 * spe + 8)])          # warm-up: captures the per-(batch, kind, slot) graphs
+    # warm-up: captures the per-(batch, kind, slot) graphs; the ragged validation batch meets every ring slot within R epochs
+    e2e_steps(items[:min(len(items), R * (spe + len(runner.val_sizes)) + 2)])
     D.barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
