@@ -68,6 +68,15 @@ __device__ __forceinline__ float elu_f(float x) {
     const float neg = x > -0.25f ? p : e;
     return x > 0.f ? x : neg;
 }
+// ELU with ABSOLUTE accuracy (~2e-7: one multiply, MUFU.EX2 in its .ftz form, one add, one compare, one select) for the
+// bandwidth-bound kernels whose output feeds a convolution or a pooling sum: there the absolute error is what counts, and
+// the 14 instructions of elu_f per element (4 ELUs per 16 loaded bytes in dw_fwd) made those kernels issue-bound.
+// Same value as elu_bwd_act up to the exp2 approximation, so forward and recomputed activations agree.
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
+}
 __device__ __forceinline__ float elu_grad_from_pre(float x) { return x > 0.f ? 1.f : __expf(x); }
 // ELU for recomputation inside gradient reductions: absolute (not relative) accuracy near zero
 __device__ __forceinline__ float elu_bwd_act(float x) { return x > 0.f ? x : __expf(x) - 1.f; }

@@ -378,13 +378,16 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
               int64_t oW2, const float4 *__restrict__ bn1, int B, int F1, int D, int C, int T,
               int elu1, float *__restrict__ y2, float *__restrict__ part, const float4 *__restrict__ bn2_pool,
               float *__restrict__ d1) {
-    extern __shared__ float w2s[];  // [D][C]
+    extern __shared__ __align__(16) float w2s[];  // [C][DMAX]: the D weights of one electrode are two 128-bit reads
     __shared__ float red[DW_THREADS / 32][2 * DMAX];
     const int n = blockIdx.z, f = blockIdx.y, m = n / B;
     const int t = (blockIdx.x * DW_THREADS + threadIdx.x) * VEC;
     const int G = F1 * D;
     const float *W2 = params + (int64_t)m * pstride + oW2 + (int64_t)f * D * C;
-    for (int i = threadIdx.x; i < D * C; i += DW_THREADS) w2s[i] = W2[i];
+    for (int i = threadIdx.x; i < DMAX * C; i += DW_THREADS) {
+        const int c = i / DMAX, dd = i - c * DMAX;
+        w2s[i] = dd < D ? W2[dd * C + c] : 0.f;
+    }
     const float4 st = bn1[(int64_t)m * F1 + f];
     __syncthreads();
     float acc[DMAX][VEC];
@@ -417,14 +420,23 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
                         float v = fmaf(a[u][e], st.z, st.w);
-                        a[u][e] = elu1 ? elu_f(v) : v;
+                        a[u][e] = elu1 ? elu_fast(v) : v;
                     }
+                    const float4 wa = *reinterpret_cast<const float4 *>(&w2s[c * DMAX]);
+                    const float4 wb = *reinterpret_cast<const float4 *>(&w2s[c * DMAX + 4]);
+                    const float wv[DMAX] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                     for (int dd = 0; dd < DMAX; ++dd)
                         if (dd < D) {
-                            const float w = w2s[dd * C + c];
+                            if (VEC == 4) {         // packed fp32: two FFMA2 instead of four FFMA, same rounding per element
+                                const float2 w2 = make_float2(wv[dd], wv[dd]);
+                                const float2 r0 = __ffma2_rn(w2, make_float2(a[u][0], a[u][1 % VEC]), make_float2(acc[dd][0], acc[dd][1 % VEC]));
+                                const float2 r1 = __ffma2_rn(w2, make_float2(a[u][2 % VEC], a[u][3 % VEC]), make_float2(acc[dd][2 % VEC], acc[dd][3 % VEC]));
+                                acc[dd][0] = r0.x; acc[dd][1 % VEC] = r0.y; acc[dd][2 % VEC] = r1.x; acc[dd][3 % VEC] = r1.y;
+                            } else {
 #pragma unroll
-                            for (int e = 0; e < VEC; ++e) acc[dd][e] = fmaf(w, a[u][e], acc[dd][e]);
+                                for (int e = 0; e < VEC; ++e) acc[dd][e] = fmaf(wv[dd], a[u][e], acc[dd][e]);
+                            }
                         }
                 }
             }
@@ -441,8 +453,8 @@ dw_fwd_kernel(const float *__restrict__ y1, const float *__restrict__ params, in
                 if (VEC == 4 && bn2_pool != nullptr) {
                     const float4 s2 = bn2_pool[(int64_t)m * G + f * D + dd];
                     d1[((int64_t)n * G + f * D + dd) * (int64_t)(T >> 2) + (t >> 2)] =
-                        0.25f * (elu_f(fmaf(acc[dd][0], s2.z, s2.w)) + elu_f(fmaf(acc[dd][1 % VEC], s2.z, s2.w)) +
-                                 elu_f(fmaf(acc[dd][2 % VEC], s2.z, s2.w)) + elu_f(fmaf(acc[dd][3 % VEC], s2.z, s2.w)));
+                        0.25f * (elu_fast(fmaf(acc[dd][0], s2.z, s2.w)) + elu_fast(fmaf(acc[dd][1 % VEC], s2.z, s2.w)) +
+                                 elu_fast(fmaf(acc[dd][2 % VEC], s2.z, s2.w)) + elu_fast(fmaf(acc[dd][3 % VEC], s2.z, s2.w)));
                 }
             }
     }
@@ -481,7 +493,7 @@ int launch_dw_fwd(const NetDims &d, const float *y1, const float *params, const 
                   float *y2, float *part, int *part_rows, const float4 *bn2_pool, float *d1, cudaStream_t st) {
     EAV_REQUIRE(d.D <= DMAX, EAV_ERR_UNSUPPORTED, "dw_fwd: D=%d > %d unsupported", d.D, DMAX);
     dim3 grid(dw_fwd_tiles(d), d.F1, d.N);
-    const size_t smem = (size_t)d.D * d.C * sizeof(float);
+    const size_t smem = (size_t)DMAX * d.C * sizeof(float);
     const int elu1 = d.variant == EAV_VARIANT_TOR;
     static int unr = -1;
     if (unr < 0) { const char *e = getenv("EAV_DWF_UNR"); unr = e ? atoi(e) : 5; }   // measured on B200: 5 -> 0.195 ms, 3: 0.203, 6: 0.209, 10: 0.256, 15: 0.434
