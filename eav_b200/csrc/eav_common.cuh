@@ -55,31 +55,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// ELU (alpha = 1) and its derivative expressed through the ACTIVATION a = elu(x):
-// x > 0 <=> a > 0, and for x <= 0: d/dx = exp(x) = a + 1.
-// expm1 for x <= 0 without libdevice's branchy expm1f (it cost ~25 predicated instructions per
-// element and made the HBM-bound kernels issue-bound): a degree-6 Taylor polynomial near zero
-// (|x| < 0.25: truncation < 2e-7 relative) and exp(x) - 1 through MUFU.EX2 elsewhere
-// (absolute error ~1e-7 on a result of magnitude >= 0.22).  Branch-free: two selects.
-__device__ __forceinline__ float elu_f(float x) {
-    const float p = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, fmaf(x, 1.3888889e-3f, 8.3333338e-3f), 4.1666668e-2f),
-                                             1.6666667e-1f), 0.5f), 1.0f);
-    const float e = __expf(x) - 1.0f;
-    const float neg = x > -0.25f ? p : e;
-    return x > 0.f ? x : neg;
-}
-// ELU with ABSOLUTE accuracy (~2e-7: one multiply, MUFU.EX2 in its .ftz form, one add, one compare, one select) for the
-// bandwidth-bound kernels whose output feeds a convolution or a pooling sum: there the absolute error is what counts, and
-// the 14 instructions of elu_f per element (4 ELUs per 16 loaded bytes in dw_fwd) made those kernels issue-bound.
-// Same value as elu_bwd_act up to the exp2 approximation, so forward and recomputed activations agree.
-__device__ __forceinline__ float elu_fast(float x) {
+// ELU (alpha = 1).  exp(x) is ONE multiply + MUFU.EX2 in its .ftz form (no denormal pre-scale / post-square as in
+// __expf; results below 2^-126 flush to zero, harmless for exp(x) - 1 and for a derivative that multiplies a gradient).
+__device__ __forceinline__ float exp_fast(float x) {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
-    return x > 0.f ? x : e - 1.f;
+    return e;
 }
-__device__ __forceinline__ float elu_grad_from_pre(float x) { return x > 0.f ? 1.f : __expf(x); }
-// ELU for recomputation inside gradient reductions: absolute (not relative) accuracy near zero
-__device__ __forceinline__ float elu_bwd_act(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// Forward activation with ABSOLUTE accuracy (~2e-7 near zero): multiply, MUFU.EX2, add, compare, select.  Every ELU of
+// the net feeds a convolution or a pooling sum, where the absolute error is what counts; a relative-accuracy expm1
+// (libdevice's: ~25 predicated instructions, a Taylor/EX2 hybrid: 14) made the bandwidth-bound kernels issue-bound
+// (4 ELUs per 16 loaded bytes in dw_fwd: 0.235 -> 0.193 ms from this change alone).  The backward kernels recompute the
+// activation with the same expression, so forward and backward see the same values.
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : exp_fast(x) - 1.f; }
+__device__ __forceinline__ float elu_grad_from_pre(float x) { return x > 0.f ? 1.f : exp_fast(x); }
+__device__ __forceinline__ float elu_bwd_act(float x) { return elu_fast(x); }
 
 // ---------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = element index / 4, key = (seed, step).

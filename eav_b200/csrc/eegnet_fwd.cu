@@ -551,8 +551,8 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t u = eb + j - e0;
-                float sj = (elu_f(fmaf(v[j].x, st.z, st.w)) + elu_f(fmaf(v[j].y, st.z, st.w)) +
-                            elu_f(fmaf(v[j].z, st.z, st.w)) + elu_f(fmaf(v[j].w, st.z, st.w))) * invp;
+                float sj = (elu_fast(fmaf(v[j].x, st.z, st.w)) + elu_fast(fmaf(v[j].y, st.z, st.w)) +
+                            elu_fast(fmaf(v[j].z, st.z, st.w)) + elu_fast(fmaf(v[j].w, st.z, st.w))) * invp;
                 if (dropout_mode == EAV_DROPOUT_MASK) sj = (u >= 0 && u < T4 && mask1[eb + j]) ? sj * inv_keep : 0.f;
                 else if (dropout_mode >= EAV_DROPOUT_PHILOX) sj = ((keep >> j) & 1u) ? sj * inv_keep : 0.f;
                 o[j] = sj;
@@ -569,7 +569,7 @@ pool1_fwd_kernel(const float *__restrict__ y2, const float4 *__restrict__ bn2,
     }
     for (int u = lane; u < T4; u += 32) {
         float s = 0.f;
-        for (int w = 0; w < P1; ++w) s += elu_f(fmaf(src[u * P1 + w], st.z, st.w));
+        for (int w = 0; w < P1; ++w) s += elu_fast(fmaf(src[u * P1 + w], st.z, st.w));
         s *= invp;
         const int64_t e = row * T4 + u;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask1[e] ? s * inv_keep : 0.f;
@@ -1029,7 +1029,7 @@ tail_fwd_kernel(const float *__restrict__ y3, const float4 *__restrict__ bn3,
         const float4 st = bn3[(int64_t)m * F2 + o];
         const float *src = y3 + ((int64_t)n * F2 + o) * T4 + v * P2;
         float s = 0.f;
-        for (int w = 0; w < P2; ++w) s += elu_f(fmaf(src[w], st.z, st.w));
+        for (int w = 0; w < P2; ++w) s += elu_fast(fmaf(src[w], st.z, st.w));
         s *= 1.f / (float)P2;
         int64_t e = (int64_t)n * FEAT + i;
         if (dropout_mode == EAV_DROPOUT_MASK) s = mask2[e] ? s * inv_keep : 0.f;
