@@ -299,6 +299,7 @@ static int run_stage(const NetDims &d, const WsLayout &w, int stage, const Stage
         case ST_BN3_BWD:
             return launch_bn_bwd_finalize(d, 3, part, d.B, W * d.B * d.T4, dp_bn ? sums(3, true) : nullptr, a.params, WS(float4, w.bnf3), WS(float4, w.bnb3), a.grads, st);
         case ST_BN3_BWD_APPLY:   // dz3 -> dy3 in place (variant 0; variant 1's pointwise kernel applies it itself)
+            if (tail_bwd_folds_bn3(d)) return 0;    // eval mode: tail_bwd already wrote dy3 = k * dz3
             if (tor) return launch_bn_bwd_apply(d, WS(float, w.dz3), WS(float, w.y3), WS(float4, w.bnf3), WS(float4, w.bnb3), st);
             return 0;
         case ST_SEPCONV_BWD_DX:

@@ -19,7 +19,11 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
                 const float *__restrict__ params, int64_t pstride, int64_t oWd, const float *__restrict__ y3,
                 const float4 *__restrict__ bn3, const uint8_t *__restrict__ mask2, int B, int F2, int T4,
                 int T32, int P2, int NC, int softmax_out, int dropout_mode, float p_drop, uint64_t seed,
-                uint64_t step, const unsigned long long *__restrict__ step_ptr, float *__restrict__ dz, float *__restrict__ dz3, float *__restrict__ part) {
+                uint64_t step, const unsigned long long *__restrict__ step_ptr, float *__restrict__ dz, float *__restrict__ dz3, float *__restrict__ part,
+                int fold_bn) {
+    // fold_bn (eval-mode BatchNorm-3, variant 0): BN backward is the per-channel scale k = gamma * invstd = bn3[].z, known
+    // before this kernel starts -- dz3 leaves as dy3 = k * g and the in-place bn_bwd_apply pass (43 MB read + write) is skipped;
+    // the d(gamma) / d(beta) sums are taken over the unscaled g as before.
     extern __shared__ float sm[];  // dfeat_s[FEAT] + dz_s[NC]
     const int FEAT = F2 * T32;
     float *dfeat_s = sm, *dz_s = sm + FEAT;
@@ -88,7 +92,7 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
                         const int v = u / P2;
                         const float y = yv[r][q];
                         const float g = (v < T32) ? dfeat_s[o * T32 + v] * elu_grad_from_pre(fmaf(y, st.z, st.w)) : 0.f;
-                        dst[u] = g;
+                        dst[u] = fold_bn ? g * st.z : g;
                         s1 += g;
                         s2 = fmaf(g, (y - st.x) * st.y, s2);
                     }
@@ -107,7 +111,7 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
             int v = u / P2;
             float y = src[u];
             float g = (v < T32) ? dfeat_s[o * T32 + v] * elu_grad_from_pre(fmaf(y, st.z, st.w)) : 0.f;
-            dst[u] = g;
+            dst[u] = fold_bn ? g * st.z : g;
             s1 += g;
             s2 = fmaf(g, (y - st.x) * st.y, s2);
         }
@@ -115,13 +119,15 @@ tail_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ probs,
     }
 }
 
+bool tail_bwd_folds_bn3(const NetDims &d) { return !d.bn_train && d.variant == EAV_VARIANT_TOR; }
+
 int launch_tail_bwd(const NetDims &d, const float *dout, const float *probs, const float *params,
                     const float *y3, const float4 *bn3, const uint8_t *mask2, float *dz, float *dz3,
                     float *part, cudaStream_t st) {
     size_t smem = (size_t)(d.FEAT + d.NC) * sizeof(float);
     tail_bwd_kernel<<<d.N, 128, smem, st>>>(dout, probs, params, d.pstride, d.oWd, y3, bn3, mask2, d.B, d.F2,
                                             d.T4, d.T32, d.P2, d.NC, d.variant == EAV_VARIANT_TOR,
-                                            d.dropout_mode, d.p_drop, d.seed, d.step, d.step_ptr, dz, dz3, part);
+                                            d.dropout_mode, d.p_drop, d.seed, d.step, d.step_ptr, dz, dz3, part, tail_bwd_folds_bn3(d) ? 1 : 0);
     EAV_CUDA_LAUNCH_CHECK("tail_bwd");
     return 0;
 }

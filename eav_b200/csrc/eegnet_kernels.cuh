@@ -11,6 +11,7 @@ namespace eav {
 // when that is 0)
 int launch_tconv_fwd(const NetDims &d, const float *x, const int32_t *x_index, const float *params,
                      float *wt_scratch, float *y1, float *part, int *part_rows, cudaStream_t st);
+bool tail_bwd_folds_bn3(const NetDims &d);   // eval mode, variant 0: dz3 leaves tail_bwd already scaled by BatchNorm-3's k
 bool tc_path_enabled(const char *var);   // false when EAV_TC or <var> is "ffma" / "0"
 // tensor-core (tcgen05) block-2 convolution, sepconv_tc.cu (mode 0 forward, 1 input gradient)
 bool sepconv_use_tc(const NetDims &d);
