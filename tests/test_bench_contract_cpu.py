@@ -38,12 +38,20 @@ def test_committed_bench_line_has_the_contract_keys():
 
 
 def test_committed_8gpu_line_is_the_42_subject_workload():
-    d = _load("r2_bench_n8_noreplica.json")
+    d = _load("r2_bench_n8.json")
     assert d["n_gpus"] == 8 and d["scaling"] == "strong"
     assert d["config"]["subjects_total"] == 42 and d["config"]["subjects_per_gpu"] == [6, 6, 5, 5, 5, 5, 5, 5]
     assert d["dp_parity"]["ok"] is True
     one = _load("r2_bench_n1.json")
     assert 4.5 < d["value"] / one["value"] <= 7.0            # strong scaling of 42 subjects: ceiling 42 / 6 = 7.0
+
+
+def test_committed_scaling_lines_are_monotonic():
+    vals = [_load(f"r2_bench_n{n}.json") for n in (1, 2, 4, 8)]
+    assert [v["n_gpus"] for v in vals] == [1, 2, 4, 8]
+    assert all(v["config"]["subjects_total"] == 42 and sum(v["config"]["subjects_per_gpu"]) == 42 for v in vals)
+    assert all(b["value"] > 1.5 * a["value"] for a, b in zip(vals, vals[1:]))      # every doubling pays at least 1.5x
+    assert all(v["dp_parity"]["ok"] for v in vals[1:])
 
 
 def test_reference_arm_line():
