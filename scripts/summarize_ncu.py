@@ -15,10 +15,11 @@ for row in csv.DictReader(lines):
     agg.setdefault(name, []).append(v)
 ours = {k: v for k, v in agg.items() if "eav::" in k}
 tot = sum(sum(v) for v in ours.values())
-with open(dst, "w") as f:
-    f.write("kernel,launches,mean_us,total_us,share_of_eav_time\n")
+with open(dst, "w", newline="") as f:
+    w = csv.writer(f)                       # kernel names contain commas (template arguments): quoted
+    w.writerow(["kernel", "launches", "mean_us", "total_us", "share_of_eav_time"])
     for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
-        f.write(f"{k},{len(v)},{sum(v)/len(v):.1f},{sum(v):.1f},{sum(v)/tot:.4f}\n")
+        w.writerow([k, len(v), f"{sum(v)/len(v):.1f}", f"{sum(v):.1f}", f"{sum(v)/tot:.4f}"])
     other = sum(sum(v) for k, v in agg.items() if "eav::" not in k)
-    f.write(f"(non-eav kernels: torch fills/copies/RNG for synthetic data),{sum(len(v) for k, v in agg.items() if 'eav::' not in k)},,{other:.1f},\n")
+    w.writerow(["(non-eav kernels: torch fills/copies/RNG for synthetic data)", sum(len(v) for k, v in agg.items() if "eav::" not in k), "", f"{other:.1f}", ""])
 print(open(dst).read())

@@ -20,10 +20,11 @@ for r in csv.DictReader(lines):
         d["wr"] += v * unit.get(u, 1)
 ours = {k: d for k, d in agg.items() if "eav::" in k}
 tot = sum(d["t"] for d in ours.values())
-with open(dst, "w") as f:
-    f.write("kernel,launches,mean_us,share_of_eav_time,dram_read_MB_per_launch,dram_write_MB_per_launch\n")
+with open(dst, "w", newline="") as f:
+    w = csv.writer(f)                       # kernel names contain commas (template arguments): quoted
+    w.writerow(["kernel", "launches", "mean_us", "share_of_eav_time", "dram_read_MB_per_launch", "dram_write_MB_per_launch"])
     for k, d in sorted(ours.items(), key=lambda kv: -kv[1]["t"]):
-        f.write(f"{k},{d['n']},{d['t'] / d['n']:.1f},{d['t'] / tot:.4f},{d['rd'] / d['n'] / 1e6:.1f},{d['wr'] / d['n'] / 1e6:.1f}\n")
+        w.writerow([k, d["n"], f"{d['t'] / d['n']:.1f}", f"{d['t'] / tot:.4f}", f"{d['rd'] / d['n'] / 1e6:.1f}", f"{d['wr'] / d['n'] / 1e6:.1f}"])
 print(open(dst).read())
 
 
