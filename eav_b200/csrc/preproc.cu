@@ -26,7 +26,8 @@ constexpr int FIR_THREADS = 256;
 constexpr int FIR_OT = FIR_R * FIR_THREADS;   // 2048 outputs per CTA tile
 constexpr int MAX_TAPS = 128;
 
-struct FirTaps { float h[MAX_TAPS]; double sum; };
+// hp[t] = (h[t], h[t + down]): the tap pair two neighbouring outputs of a thread apply to the same input sample (packed FFMA2)
+struct FirTaps { float h[MAX_TAPS]; float2 hp[MAX_TAPS]; double sum; };
 
 // Tile loader: xs[s] = x_seq[i0 + s] for s in [0, n_in), zero outside the record.  The
 // continuous index is mapped to (trial, offset) ONCE per thread and then advanced
@@ -97,36 +98,53 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 // II = offset of one staged input sample relative to x[DOWN*j - H]; for each of the FIR_R
 // outputs of the thread the tap index t = DOWN*r + 2H - II is a constant, so every FFMA
 // takes its tap from a uniform register.
-template <int DOWN, int NTAPS, bool SKIP, int II>
-__device__ __forceinline__ void fir_one_input(const FirTaps &taps, float v, float (&acc0)[FIR_R], float (&acc1)[FIR_R]) {
+template <int DOWN, int NTAPS, bool SKIP, int T>
+__device__ __forceinline__ constexpr bool fir_tap_live() {
     constexpr int H = (NTAPS - 1) / 2;
+    return T >= 0 && T < NTAPS && !(SKIP && T != H && ((T - H) % DOWN) == 0);
+}
+// Outputs r and r + 1 of a thread see the same input sample through taps t and t + DOWN: one packed FFMA2 (Blackwell
+// fma.rn.f32x2; the tap pair comes from the constant bank through a uniform register pair, the input is a broadcast
+// scalar operand) instead of two FFMA.  Same products, same accumulation order per output as the scalar form.
+template <int DOWN, int NTAPS, bool SKIP, int II, int R>
+__device__ __forceinline__ void fir_pair(const FirTaps &taps, float v, float2 (&acc)[FIR_R / 2]) {
+    constexpr int H = (NTAPS - 1) / 2;
+    constexpr int t = DOWN * R + 2 * H - II, t2 = t + DOWN;
+    constexpr bool l0 = fir_tap_live<DOWN, NTAPS, SKIP, t>(), l1 = fir_tap_live<DOWN, NTAPS, SKIP, t2>();
+    if constexpr (l0 && l1) acc[R / 2] = __ffma2_rn(taps.hp[t], make_float2(v, v), acc[R / 2]);
+    else if constexpr (l0) acc[R / 2].x = fmaf(taps.h[t], v, acc[R / 2].x);
+    else if constexpr (l1) acc[R / 2].y = fmaf(taps.h[t2], v, acc[R / 2].y);
+}
+template <int DOWN, int NTAPS, bool SKIP, int II>
+__device__ __forceinline__ void fir_one_input(const FirTaps &taps, float v, float2 (&acc0)[FIR_R / 2], float2 (&acc1)[FIR_R / 2]) {
+    static_assert(FIR_R == 8, "fir_one_input is written for 8 outputs per thread");
     if constexpr (II >= 0) {
-#pragma unroll
-        for (int r = 0; r < FIR_R; ++r) {
-            const int t = DOWN * r + 2 * H - II;
-            const bool zero_tap = SKIP && t != H && ((t - H) % DOWN) == 0;
-            if (t >= 0 && t < NTAPS && !zero_tap) {
-                if (II & 1) acc1[r] = fmaf(taps.h[t], v, acc1[r]);
-                else acc0[r] = fmaf(taps.h[t], v, acc0[r]);
-            }
+        if constexpr (II & 1) {
+            fir_pair<DOWN, NTAPS, SKIP, II, 0>(taps, v, acc1); fir_pair<DOWN, NTAPS, SKIP, II, 2>(taps, v, acc1);
+            fir_pair<DOWN, NTAPS, SKIP, II, 4>(taps, v, acc1); fir_pair<DOWN, NTAPS, SKIP, II, 6>(taps, v, acc1);
+        } else {
+            fir_pair<DOWN, NTAPS, SKIP, II, 0>(taps, v, acc0); fir_pair<DOWN, NTAPS, SKIP, II, 2>(taps, v, acc0);
+            fir_pair<DOWN, NTAPS, SKIP, II, 4>(taps, v, acc0); fir_pair<DOWN, NTAPS, SKIP, II, 6>(taps, v, acc0);
         }
     }
 }
 template <int DOWN, int NTAPS, bool SKIP, int LEAD, int Q, int NQ>
 struct FirSteps {
-    static __device__ __forceinline__ void run(const FirTaps &taps, const float *xw, float m, float (&acc0)[FIR_R],
-                                               float (&acc1)[FIR_R]) {
+    static __device__ __forceinline__ void run(const FirTaps &taps, const float *xw, float m, float2 (&acc0)[FIR_R / 2],
+                                               float2 (&acc1)[FIR_R / 2]) {
         const float4 v4 = *reinterpret_cast<const float4 *>(xw + 4 * Q);
-        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 0 - LEAD>(taps, v4.x - m, acc0, acc1);
-        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 1 - LEAD>(taps, v4.y - m, acc0, acc1);
-        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 2 - LEAD>(taps, v4.z - m, acc0, acc1);
-        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 3 - LEAD>(taps, v4.w - m, acc0, acc1);
+        const float2 nm = make_float2(-m, -m);
+        const float2 a = __fadd2_rn(make_float2(v4.x, v4.y), nm), b = __fadd2_rn(make_float2(v4.z, v4.w), nm);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 0 - LEAD>(taps, a.x, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 1 - LEAD>(taps, a.y, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 2 - LEAD>(taps, b.x, acc0, acc1);
+        fir_one_input<DOWN, NTAPS, SKIP, 4 * Q + 3 - LEAD>(taps, b.y, acc0, acc1);
         FirSteps<DOWN, NTAPS, SKIP, LEAD, Q + 1, NQ>::run(taps, xw, m, acc0, acc1);
     }
 };
 template <int DOWN, int NTAPS, bool SKIP, int LEAD, int NQ>
 struct FirSteps<DOWN, NTAPS, SKIP, LEAD, NQ, NQ> {
-    static __device__ __forceinline__ void run(const FirTaps &, const float *, float, float (&)[FIR_R], float (&)[FIR_R]) {}
+    static __device__ __forceinline__ void run(const FirTaps &, const float *, float, float2 (&)[FIR_R / 2], float2 (&)[FIR_R / 2]) {}
 };
 
 // Fully unrolled decimating FIR: DOWN and NTAPS are compile-time so every tap index is
@@ -197,15 +215,18 @@ fir_decimate_kernel(const TIn *__restrict__ raw, const __grid_constant__ FirTaps
     if (jl >= tile_out) return;
     const float *xw = xs + DOWN * jl;                          // 16B aligned: DOWN*FIR_R % 4 == 0
     const float m = xw[LEAD];
-    float acc0[FIR_R], acc1[FIR_R];
+    float2 acc0[FIR_R / 2], acc1[FIR_R / 2];          // even / odd input samples; element r/2 = outputs (r, r + 1)
 #pragma unroll
-    for (int r = 0; r < FIR_R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+    for (int r = 0; r < FIR_R / 2; ++r) { acc0[r] = make_float2(0.f, 0.f); acc1[r] = make_float2(0.f, 0.f); }
     FirSteps<DOWN, NTAPS, SKIP, LEAD, 0, WIN4 / 4>::run(taps, xw, m, acc0, acc1);
     float *dst = dec + ((int64_t)s * n_chans + c) * n_dec + j0 + jl;
     const double md = (double)m * taps.sum;
     float o[FIR_R];
 #pragma unroll
-    for (int r = 0; r < FIR_R; ++r) o[r] = (float)((double)(acc0[r] + acc1[r]) + md);
+    for (int r = 0; r < FIR_R; ++r) {
+        const float a0 = (r & 1) ? acc0[r >> 1].y : acc0[r >> 1].x, a1 = (r & 1) ? acc1[r >> 1].y : acc1[r >> 1].x;
+        o[r] = (float)((double)(a0 + a1) + md);
+    }
     if (jl + FIR_R <= tile_out && j0 + jl + FIR_R <= n_dec && ((n_dec | tile_out) & 3) == 0) {
         reinterpret_cast<float4 *>(dst)[0] = make_float4(o[0], o[1], o[2], o[3]);
         reinterpret_cast<float4 *>(dst)[1] = make_float4(o[4], o[5], o[6], o[7]);
@@ -556,6 +577,13 @@ static int check_cfg(const eav_preproc_cfg *c) {
     return 0;
 }
 
+// EAV_SOS_STATE=dot: pass 1 of the exact scan as a table dot product (needs the G table, built on the host per call)
+static bool sos_state_use_dot() {
+    static int use_dot = -1;
+    if (use_dot < 0) { const char *e = getenv("EAV_SOS_STATE"); use_dot = (e && strcmp(e, "dot") == 0) ? 1 : 0; }
+    return use_dot != 0;
+}
+
 template <int NSEC>
 static int run_sos(const eav_preproc_cfg *c, const float *dec, const SosCoef &co, const CarryMat &A,
                    const double *gtab, const int32_t *kept, int n_kept, double *z, double *start,
@@ -568,9 +596,7 @@ static int run_sos(const eav_preproc_cfg *c, const float *dec, const SosCoef &co
     // table dot product 1.05 ms -- the dot product needs 5 broadcast LDS.128 per sample and a broadcast
     // LDS still costs 512 B of register write-back per warp (128 B/clk/SM), which outweighs the 2.5x
     // fewer DFMAs.  The recurrence stays the default; EAV_SOS_STATE=dot selects the other one.
-    static int use_dot = -1;
-    if (use_dot < 0) { const char *e = getenv("EAV_SOS_STATE"); use_dot = (e && strcmp(e, "dot") == 0) ? 1 : 0; }
-    if (use_dot)
+    if (sos_state_use_dot())
         sos_state_dot_kernel<NSEC><<<(unsigned)cdiv64(work1, SOS_THREADS), SOS_THREADS, 0, st>>>(dec, gtab, c->n_trials, chunk,
                                                                                                 n_dec, z, work1);
     else
@@ -705,6 +731,7 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
     memset(&ft, 0, sizeof(ft));
     double hs = 0.0;
     for (int t = 0; t < cfg->n_taps; ++t) { ft.h[t] = (float)taps[t]; hs += (double)ft.h[t]; }
+    for (int t = 0; t + cfg->down < cfg->n_taps; ++t) ft.hp[t] = make_float2(ft.h[t], ft.h[t + cfg->down]);
     ft.sum = hs;
 
     // SOS coefficients and the zero-input transition matrix A^L of the cascade (host, fp64)
@@ -755,8 +782,10 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
     }
     // G[j] = A1^j b for j in [0, chunk): b = state after feeding a unit sample into the cascade at rest,
     // A1 = the one-step zero-input matrix (recomputed here: the squaring above overwrote it).
+    // Only the (non-default) dot-product form of pass 1 reads it: building it costs ~1 ms of host time per call and its
+    // pageable upload synchronises the stream -- with it built unconditionally the GPU idled 0.6 ms of every 3.2 ms run.
     double *gtab = reinterpret_cast<double *>(ws + l.gtab);
-    {
+    if (sos_state_use_dot() && !bp_first) {
         std::vector<long double> A1((size_t)NS * NS), g(NS), gn(NS);
         for (int e = 0; e <= NS; ++e) {            // e == NS: unit input from rest -> b
             long double s0[MAX_SEC] = {0}, s1[MAX_SEC] = {0};
