@@ -278,7 +278,13 @@ struct CarryMat { double a[4 * MAX_SEC * MAX_SEC]; };   // (2*NSEC)^2 row-major
 constexpr int SOS_THREADS = 128;
 constexpr int SOS_TILE = 32;
 
-template <int NSEC, bool APPLY>
+// numerator patterns of the 5-section Butterworth band-pass (b = b0 * (1, c1, c2)); PAT 0 = general coefficients
+__host__ __device__ constexpr int sos_pat_c1(int pat, int k) {
+    return (k == 2 || k > 4) ? 0 : ((k < 2) == (pat == 1) ? 2 : -2);
+}
+__host__ __device__ constexpr int sos_pat_c2(int, int k) { return k == 2 ? -1 : 1; }
+
+template <int NSEC, bool APPLY, int PAT = 0>
 __global__ void __launch_bounds__(SOS_THREADS)
 sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, int n_chans, int n_trials,
            int chunk_len, int64_t n_dec, const int32_t *__restrict__ kept_trial, int n_kept,
@@ -367,10 +373,23 @@ sos_kernel(const float *__restrict__ dec, const __grid_constant__ SosCoef co, in
                 double x = (double)tile[tid][i];
 #pragma unroll
                 for (int k = 0; k < NSEC; ++k) {
-                    double y = fma(co.b0[k], x, s0[k]);
-                    s0[k] = fma(co.b1[k], x, fma(-co.a1[k], y, s1[k]));
-                    s1[k] = fma(co.b2[k], x, -co.a2[k] * y);
-                    x = y;
+                    if (PAT != 0) {
+                        // Butterworth band-pass numerators (PAT 1: (z+1)^2, (z+1)^2, z^2-1, (z-1)^2, (z-1)^2; PAT 2: mirrored),
+                        // gain in section 0, checked on the host: 20 fp64 operations per sample instead of 25 -- the kernel
+                        // is bound by the fp64 pipe.  b1 * x = +-2u is one DFMA with a literal, b2 * x = +-u a negation.
+                        const int c1 = sos_pat_c1(PAT, k), c2 = sos_pat_c2(PAT, k);
+                        const double u = k == 0 ? co.b0[0] * x : x;
+                        const double y = u + s0[k];
+                        const double t = c1 == 0 ? s1[k] : fma((double)c1, u, s1[k]);
+                        s0[k] = fma(-co.a1[k], y, t);
+                        s1[k] = fma(-co.a2[k], y, c2 < 0 ? -u : u);
+                        x = y;
+                    } else {
+                        double y = fma(co.b0[k], x, s0[k]);
+                        s0[k] = fma(co.b1[k], x, fma(-co.a1[k], y, s1[k]));
+                        s1[k] = fma(co.b2[k], x, -co.a2[k] * y);
+                        x = y;
+                    }
                 }
                 if (emit) tile[tid][i] = (float)x;
             }
@@ -743,6 +762,20 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
         EAV_REQUIRE(r[3] == 1.0, EAV_ERR_UNSUPPORTED, "preproc_run: sos a0 must be 1 (scipy normalises it)");
         co.b0[k] = r[0]; co.b1[k] = r[1]; co.b2[k] = r[2]; co.a1[k] = r[4]; co.a2[k] = r[5];
     }
+    // numerator pattern of the 5-section Butterworth band-pass (exact comparisons): b = b0 * (1, c1, c2), b0 = 1 for k > 0
+    int sos_pat = 0;
+    if (NSEC == 5) {
+        for (int pat = 1; pat <= 2 && sos_pat == 0; ++pat) {
+            bool ok = true;
+            for (int k = 0; k < NSEC; ++k) {
+                const double b0 = co.b0[k];
+                ok = ok && co.b1[k] == (double)sos_pat_c1(pat, k) * b0 && co.b2[k] == (double)sos_pat_c2(pat, k) * b0 &&
+                     (k == 0 || b0 == 1.0);
+            }
+            if (ok) sos_pat = pat;
+        }
+    }
+    { const char *e = getenv("EAV_SOS_PATTERN"); if (e && e[0] == '0') sos_pat = 0; }
     const bool bp_first = cfg->order == EAV_PREPROC_ORDER_BANDPASS_FIRST;
     const int chunk = cfg->trial_len / cfg->down;               // decimated samples per trial
     const int sos_chunk = bp_first ? cfg->trial_len : chunk;    // samples per trial at the rate the SOS runs at
@@ -904,19 +937,25 @@ extern "C" int eav_preproc_run(const eav_preproc_cfg *cfg, const void *raw, cons
                 const int64_t work = (int64_t)sub.n_subjects * cfg->n_chans * n_kept;
                 const int32_t *kept_g = kept + (size_t)s0 * n_kept;
                 float *ep_g = epochs + s0 * ep_subj_e;
-#define EAV_WARM(NS_)                                                                                               \
-    sos_kernel<NS_, true><<<(unsigned)cdiv64(work, SOS_THREADS), SOS_THREADS, 0, sst>>>(                            \
+#define EAV_WARM_P(NS_, PAT_)                                                                                       \
+    sos_kernel<NS_, true, PAT_><<<(unsigned)cdiv64(work, SOS_THREADS), SOS_THREADS, 0, sst>>>(                      \
         dec_g, co, cfg->n_chans, cfg->n_trials, chunk, n_dec, kept_g, n_kept, nullptr, nullptr, cfg->n_sub,         \
         chunk / cfg->n_sub, n_epochs_out, ep_g, work, 0, 1)
+#define EAV_WARM(NS_) EAV_WARM_P(NS_, 0)
                 switch (NSEC) {
                     case 1: EAV_WARM(1); break;
                     case 2: EAV_WARM(2); break;
                     case 3: EAV_WARM(3); break;
                     case 4: EAV_WARM(4); break;
-                    case 5: EAV_WARM(5); break;
+                    case 5:
+                        if (sos_pat == 1) EAV_WARM_P(5, 1);
+                        else if (sos_pat == 2) EAV_WARM_P(5, 2);
+                        else EAV_WARM(5);
+                        break;
                     default: EAV_WARM(6); break;
                 }
 #undef EAV_WARM
+#undef EAV_WARM_P
                 EAV_CUDA_LAUNCH_CHECK("sos_warm_apply");
             }
             if (sd != nullptr) {
