@@ -96,6 +96,26 @@ def test_dataset_shaped_subjects_vs_oracle_and_reference_digest(golden, subject_
         xo, yo = O.prepare_data(raws[s], labels[s], [0.5, 45])
         assert _chan_rel_err(ep[s], xo) < TOL, s
 
+def test_band_pass_pattern_kernel_equals_general_kernel(subject_pair, monkeypatch):
+    """The Butterworth band-pass numerators b0*(1, +-2, 1) / (1, 0, -1) select a kernel instance with the pattern compiled in
+    (20 instead of 25 fp64 operations per sample); EAV_SOS_PATTERN=0 forces the general instance.  Same fp64
+    products up to the order of two additions: the float32 epochs agree to rounding."""
+    import eeg_oracle as O
+    from eav_b200.ops import PreprocEngine
+    raws, labels = subject_pair
+    taps = O.decimation_taps(5)
+    slot = torch.from_numpy(np.stack([_slots(O.epoch_plan(l)[0]) for l in labels])).cuda()
+    raw = torch.from_numpy(raws).cuda()
+    eng = PreprocEngine(2)
+    for band in ([0.5, 45], [1, 40]):                 # both take the forgetting-filter path
+        sos = O.butter_sos(band, 100.0)
+        assert np.array_equal(sos[1:, 0], np.ones(4)) and np.array_equal(np.abs(sos[:, 1] / sos[:, 0]), [2, 2, 0, 2, 2])
+        monkeypatch.delenv("EAV_SOS_PATTERN", raising=False)
+        a = eng.run(raw, taps, sos, slot, 400).cpu().numpy()
+        monkeypatch.setenv("EAV_SOS_PATTERN", "0")
+        b = eng.run(raw, taps, sos, slot, 400).cpu().numpy()
+        assert _chan_rel_err(a[0], b[0].astype(np.float64)) < 1e-6 and _chan_rel_err(a[1], b[1].astype(np.float64)) < 1e-6
+
 
 def test_legacy_order_small_vs_oracle():
     """order=1: band-pass at fs_orig over the raw recording, then decimate (CNN_EEG_tf.py:64-75,182-189)."""
