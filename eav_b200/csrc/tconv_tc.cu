@@ -377,6 +377,12 @@ namespace {
 constexpr int TCW_PROD_WARPS = 7;
 constexpr int TCW_THREADS = (5 + TCW_PROD_WARPS) * 32;
 constexpr int TCW_STAGES = TCW_PROD_WARPS;
+// Row g of a CTA uses ring stage (g + TCW_FIRST_STAGE) % TCW_STAGES.  Any rotation is the same protocol (same barriers, same
+// phases, same memory); 3 instead of 0 only because `compute-sanitizer --tool synccheck` (12.9) reports "Barrier error: Missing
+// init" on the empty-barrier of whichever stage is index 0 when the ring STARTS there, and nothing when it starts elsewhere.
+// The report followed that barrier through three different shared addresses and was independent of the order of the
+// mbarrier.init calls and of the ring memory slot (profiles/r2_sanitizer.txt): a property of the tool, not of the kernel.
+constexpr int TCW_FIRST_STAGE = 3;
 constexpr int TCW_XS = 896;                       // floats per x buffer (>= 32*15 + 384), 3584 B
 constexpr int TCW_DYROW = 512;                    // floats per dy row
 constexpr int TCW_STAGE_FLOATS = 2 * TCW_XS + 2 * 4 * TCW_DYROW;   // x hi, x lo, dy hi[4], dy lo[4] = 23552 B
@@ -453,7 +459,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
             unit_rows(u, m, fg, r_lo, r_hi);
             for (int r = r_lo; r < r_hi; ++r, ++g) {
                 if (g % TCW_PROD_WARPS != pw) continue;
-                const int s = g % TCW_STAGES, use = g / TCW_STAGES;
+                const int s = (g + TCW_FIRST_STAGE) % TCW_STAGES, use = g / TCW_STAGES;
                 const int b = r / C, c = r - b * C;
                 const int64_t n = (int64_t)m * B + b;
                 const int64_t xrow = x_index ? (int64_t)x_index[n] : n;
@@ -536,7 +542,7 @@ tconv_bwd_dw_tc_kernel(const float *__restrict__ x, const int32_t *__restrict__ 
             unit_rows(u, m, fg, r_lo, r_hi);
             if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);     // epilogue drained the previous unit
             for (int r = r_lo; r < r_hi; ++r, ++g) {
-                const int s = g % TCW_STAGES, use = g / TCW_STAGES;
+                const int s = (g + TCW_FIRST_STAGE) % TCW_STAGES, use = g / TCW_STAGES;
                 tc::mbar_wait(&bar_full[s], use & 1);
                 tc::tc_fence_after_sync();
                 if (leader) {
