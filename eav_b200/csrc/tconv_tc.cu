@@ -914,6 +914,8 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
             // ---------------- MMA issuer (as in tconv_bwd_dw_tc_kernel) ----------------
             const bool leader = tc::elect_one();
             const uint32_t idesc = tc::idesc_tf32(128, 128, 1, 1);
+            const uint64_t xdesc0 = desc_mn_sw(tc::smem_u32(ring), 128, 512);                            // stage 0: x hi
+            const uint64_t ddesc0 = desc_mn_sw(tc::smem_u32(ring) + 4u * 2 * TCW_XS, 4 * TCW_DYROW, 512);   // stage 0: dz1 hi
             int g = 0, nu = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
                 int m, fg, r_lo, r_hi;
@@ -924,20 +926,19 @@ tconv_bwd_fused_tc_kernel(const float *__restrict__ x, const int32_t *__restrict
                     tc::mbar_wait_sleep(&bar_full[s], use & 1, 40);
                     tc::tc_fence_after_sync();
                     if (leader) {
-                        const uint32_t sbase = tc::smem_u32(ring + (size_t)s * TCW_STAGE_FLOATS);
-                        const uint32_t xhi = sbase, xlo = sbase + 4u * TCW_XS;
-                        const uint32_t dyhi = sbase + 4u * 2 * TCW_XS, dylo = dyhi + 4u * 4 * TCW_DYROW;
+                        // descriptors = hoisted stage-0 descriptors + address-field offsets (16-byte units): this warp shares a
+                        // scheduler with two producer warps, every instruction it does not issue is a slot for them
+                        const uint64_t so = (uint64_t)((uint32_t)s * ((TCW_STAGE_FLOATS * 4) >> 4));
+                        const uint64_t xh = xdesc0 + so, xl = xh + ((4 * TCW_XS) >> 4);
+                        const uint64_t dh = ddesc0 + so, dl = dh + ((4 * 4 * TCW_DYROW) >> 4);
                         const uint32_t first = (r == r_lo) ? 0u : 1u;
                         for (int mt = 0; mt < mtiles; ++mt) {
                             const uint32_t d = tmem + mt * 128;
                             for (int ks = 0; ks < ksteps; ++ks) {
-                                const uint32_t ao = mt * 512 + ks * 1024, bo = ks * 1024;
-                                const uint64_t ah = desc_mn_sw(xhi + ao, 128, 512), al = desc_mn_sw(xlo + ao, 128, 512);
-                                const uint64_t bh = desc_mn_sw(dyhi + bo, 4 * TCW_DYROW, 512);
-                                const uint64_t bl = desc_mn_sw(dylo + bo, 4 * TCW_DYROW, 512);
-                                tc::mma_tf32_ss(d, ah, bh, idesc, (ks > 0) ? 1u : first);
-                                tc::mma_tf32_ss(d, ah, bl, idesc, 1u);
-                                tc::mma_tf32_ss(d, al, bh, idesc, 1u);
+                                const uint32_t ao = mt * 32 + ks * 64, bo = ks * 64;
+                                tc::mma_tf32_ss(d, xh + ao, dh + bo, idesc, (ks > 0) ? 1u : first);
+                                tc::mma_tf32_ss(d, xh + ao, dl + bo, idesc, 1u);
+                                tc::mma_tf32_ss(d, xl + ao, dh + bo, idesc, 1u);
                             }
                         }
                         tc::mma_commit(&bar_empty[s]);
