@@ -213,9 +213,17 @@ def cpu_train_reference(steps, warmup, variant="tor", schedule="reference"):
         ns = ref_shim.load()
         torch.manual_seed(1)
         model = ref_shim.make_eegnet_tor(ns, nb_classes=5)
-        with contextlib.redirect_stdout(io.StringIO()):
-            tr = ns.EEGNet_tor.Trainer_uni(model, data=data, lr=1e-5, batch_size=BATCH, num_epochs=1,
-                                           device=torch.device("cpu"))
+        # The CPU arm must not see the GPUs: the stock constructor wraps the model in nn.DataParallel whenever
+        # torch.cuda.device_count() > 1 (EEGNet_tor.py:85-87), which then refuses CPU parameters -- on a multi-GPU box
+        # an N=1 run (cpu_baseline) or the reference arm would die here.
+        real_count = torch.cuda.device_count
+        torch.cuda.device_count = lambda: 0
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                tr = ns.EEGNet_tor.Trainer_uni(model, data=data, lr=1e-5, batch_size=BATCH, num_epochs=1,
+                                               device=torch.device("cpu"))
+        finally:
+            torch.cuda.device_count = real_count
 
         def one_step(batch):
             d, t = batch

@@ -58,3 +58,25 @@ def test_reference_arm_line():
     d = _load("r2_bench_ref.json")
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "reference" and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_cpu_arm_survives_a_multi_gpu_box(monkeypatch):
+    """The stock Trainer_uni wraps its model in nn.DataParallel when it sees more than one GPU (EEGNet_tor.py:85-87); the CPU arm
+    of bench.py (cpu_baseline at N=1, --impl reference) must not, or an N=1 run on an 8-GPU box dies in the baseline leg."""
+    import importlib.util
+    import sys
+
+    import pytest
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference sources not present (oracle/_ref or /root/reference)")
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(torch.cuda, "device_count", lambda: 8)
+    monkeypatch.setattr(bench, "_host_threads", lambda: 4)          # one thread-count candidate: keeps the test short
+    r = bench.cpu_train_reference(1, 1)
+    assert r["kind"] == "reference" and r["value"] > 0
+    assert torch.cuda.device_count() == 8                            # the patch inside was undone
