@@ -13,6 +13,7 @@ the resident dataset form the batch), exactly what the reference's DataLoader pr
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -317,6 +318,8 @@ class EpochRunner:
         self.val_acc = torch.zeros(M, 2, dtype=torch.float64, device=dev)
         self.history = torch.zeros(self.max_epochs, M, 3, dtype=torch.float32, device=dev)
         self._graphs = {}
+        if os.environ.get("EAV_PIPELINE_VAL") in ("0", "1"):           # A/B switch for measurements
+            pipeline_validation = os.environ["EAV_PIPELINE_VAL"] == "1"
         self.pipeline = bool(pipeline_validation) and len(self.val_sizes) > 0
         self._val_pending = False
         if self.pipeline:
