@@ -134,7 +134,7 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
                     }
                 }
             }
-            if (lp > 0) tc::mbar_wait(&bar_actempty, (lp - 1) & 1);
+            if (lp > 0) tc::mbar_wait_sleep(&bar_actempty, (lp - 1) & 1, 200);      // a whole pair's MMAs away: sleep, do not spin
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (s < cnt) {
@@ -173,7 +173,7 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
                 const float *wsrc = wt_packed + (int64_t)m * SCT_NBLOCKS * SCT_BLOCK;
                 for (int it = 0; it < SCT_NITER; ++it, ++g) {
                     const int st = g % SCT_WSTAGES, use = g / SCT_WSTAGES;
-                    if (use > 0) tc::mbar_wait(&bar_wempty[st], (use - 1) & 1);
+                    if (use > 0) tc::mbar_wait_sleep(&bar_wempty[st], (use - 1) & 1, 40);
                     tc::mbar_expect_tx(&bar_wfull[st], SCT_BPS * SCT_BLOCK * 4);
                     tc::tma_load_1d(wring + (size_t)st * SCT_BPS * SCT_BLOCK, wsrc + (size_t)it * SCT_BPS * SCT_BLOCK,
                                     SCT_BPS * SCT_BLOCK * 4, &bar_wfull[st]);
@@ -190,8 +190,8 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
             int m, n0, cnt;
             pair_samples(p_lo + lp, m, n0, cnt);
             const int buf = lp & 1;
-            tc::mbar_wait(&bar_actfull, lp & 1);
-            if (lp >= 2) tc::mbar_wait(&bar_accempty[buf], ((lp >> 1) - 1) & 1);
+            tc::mbar_wait_sleep(&bar_actfull, lp & 1, 40);
+            if (lp >= 2) tc::mbar_wait_sleep(&bar_accempty[buf], ((lp >> 1) - 1) & 1, 40);
             for (int it = 0; it < SCT_NITER; ++it, ++g) {
                 const int st = g % SCT_WSTAGES, use = g / SCT_WSTAGES;
                 tc::mbar_wait(&bar_wfull[st], use & 1);
@@ -229,7 +229,7 @@ sepconv_tc_kernel(const float *__restrict__ in, const float *__restrict__ wt_pac
             int m, n0, cnt;
             pair_samples(p_lo + lp, m, n0, cnt);
             const int buf = lp & 1;
-            tc::mbar_wait(&bar_accfull[buf], (lp >> 1) & 1);
+            tc::mbar_wait_sleep(&bar_accfull[buf], (lp >> 1) & 1, 200);
             tc::tc_fence_after_sync();
             for (int s = 0; s < cnt; ++s) {
                 float *dst = out + (int64_t)(n0 + s) * SCT_C * U + u;
@@ -342,7 +342,7 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
             unit_range(u, m, b_lo, b_hi);
             for (int b = b_lo; b < b_hi; ++b, ++ns) {
                 const float *sdy = stg + (size_t)(ns & 1) * 2 * SDW_STG, *sd1 = sdy + SDW_STG;
-                tc::mbar_wait(&bar_stgfull[ns & 1], (ns >> 1) & 1);
+                tc::mbar_wait_sleep(&bar_stgfull[ns & 1], (ns >> 1) & 1, 40);
                 for (int c = 0; c < n_chunks; ++c, ++g) {
                     const int st = g % SDW_STAGES, use = g / SDW_STAGES;
                     if (use > 0) tc::mbar_wait(&bar_empty[st], (use - 1) & 1);
@@ -400,7 +400,7 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
                 unit_range(u, m, b_lo, b_hi);
                 for (int b = b_lo; b < b_hi; ++b, ++ns) {
                     const int sb = ns & 1;
-                    if (ns >= 2) tc::mbar_wait(&bar_stgempty[sb], ((ns >> 1) - 1) & 1);
+                    if (ns >= 2) tc::mbar_wait_sleep(&bar_stgempty[sb], ((ns >> 1) - 1) & 1, 100);
                     const int64_t n = (int64_t)m * B + b;
                     float *dst = stg + (size_t)sb * 2 * SDW_STG;
                     tc::mbar_expect_tx(&bar_stgfull[sb], 2 * bytes);
@@ -417,7 +417,7 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
             int m, b_lo, b_hi;
             unit_range(u, m, b_lo, b_hi);
-            if (nu > 0) tc::mbar_wait(&bar_accempty, (nu - 1) & 1);
+            if (nu > 0) tc::mbar_wait_sleep(&bar_accempty, (nu - 1) & 1, 100);
             const int total = (b_hi - b_lo) * n_chunks;
             for (int ci = 0; ci < total; ++ci, ++g) {
                 const int st = g % SDW_STAGES, use = g / SDW_STAGES;
@@ -452,7 +452,7 @@ sepconv_dw_tc_kernel(const float *__restrict__ dy3, const float *__restrict__ d1
         const int m_idx = warp * 32 + lane;
         const int sa = m_idx >> 6, o = m_idx & 63;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++nu) {
-            tc::mbar_wait(&bar_accfull, nu & 1);
+            tc::mbar_wait_sleep(&bar_accfull, nu & 1, 400);     // a whole unit away (ncu: 1.7 M polls per launch while spinning)
             tc::tc_fence_after_sync();
             float *pu = part + (int64_t)u * 16 * 4096;
 #pragma unroll 1
