@@ -985,7 +985,7 @@ def run_subject_workload(args, variant):
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_total_ms / K,
                     "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
                     "how": "the same K steps (+ validation batches) with every batch in pinned host memory: "
-                           "cudaMemcpyAsync on a copy stream into double-buffered staging areas -> "
+                           "cudaMemcpyAsync on one copy stream per batch kind into 3-deep staging rings -> "
                            "eav_eegnet_forward/loss/backward/adam through the C ABI (per-step CUDA graphs; the validation "
                            "batches of an epoch run on a parameter snapshot on a second stream, overlapping the next "
                            "epoch's steps) -> loss (and #correct) D2H every step; bytes are summed over all ranks"},
